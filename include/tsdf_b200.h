@@ -1,0 +1,140 @@
+/*
+ * tsdf_b200.h -- C ABI of libtsdf_b200.so: B200 (sm_100a) TSDF integration into a dense brick
+ * grid and into a voxel-block hash map.
+ *
+ * This is the drop-in boundary for the mapping hot path of DiWu9/Union-Thesis-SLAM.  Every entry
+ * point names the reference interface it replaces (file:line under the reference root).  Plain C
+ * types only (pointers + sizes): bind with ctypes / cffi / a 50-line extension; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (TSDF_OK) or a negative tsdf_status; tsdf_last_error() gives the
+ *     text of the calling thread's last failure.  There is NO CPU fallback: without a usable CUDA
+ *     device create() fails with TSDF_ERR_NO_DEVICE.
+ *   - a handle is one rank's shard, bound to one CUDA device and one stream; not thread-safe.
+ *   - integrate() is stream-ordered and may return before the kernels finish; download / stats /
+ *     sync wait.  Host frame buffers are borrowed only for the duration of the call.
+ *   - frames: rgb = H*W*3 uint8 (R,G,B), depth = H*W float64 metres with 0 = invalid,
+ *     K = 3x3 row-major intrinsics, Tinv = 4x4 row-major float64 inverse of the camera->world pose
+ *     (the host computes np.linalg.inv(cam_pose) exactly like grid_fusion.py:265 and passes it
+ *     down; the device never inverts a pose), obs_weight > 0.
+ *   - voxel arithmetic follows the reference CPU path bit for bit.
+ */
+#ifndef TSDF_B200_H
+#define TSDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tsdf_status {
+    TSDF_OK = 0,
+    TSDF_ERR_BAD_ARG = -1,
+    TSDF_ERR_NO_DEVICE = -2,
+    TSDF_ERR_CUDA = -3,
+    TSDF_ERR_OOM = -4,
+    TSDF_ERR_HEAP_EXHAUSTED = -5, /* voxel-block heap has no free block left */
+    TSDF_ERR_TABLE_FULL = -6,     /* hash table probe sequence exhausted */
+    TSDF_ERR_CANDIDATES = -7      /* per-frame candidate / visible list overflow */
+} tsdf_status;
+
+typedef struct tsdf_grid tsdf_grid; /* opaque: dense brick grid shard */
+typedef struct tsdf_hash tsdf_hash; /* opaque: voxel-block hash map shard */
+
+#define TSDF_BRICK 8          /* voxels per brick edge (8^3 = 512 voxels) */
+#define TSDF_BRICK_FLOATS 1536 /* one brick record: 512 tsdf | 512 weight | 512 colour, float32 */
+
+const char *tsdf_last_error(void);
+/* Library / device facts: sm count, HBM bytes, compiled arch.  No handle needed. */
+int tsdf_device_info(int device, int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense grid.  Replaces grid_fusion.TSDFVolume (grid_fusion.py:19-320).
+ * --------------------------------------------------------------------------------------------- */
+
+/* TSDFVolume.__init__ (grid_fusion.py:22-57): dim = _vol_dim, origin = _vol_origin (float32),
+ * voxel_size, trunc = _trunc_margin.  State starts at tsdf=1, weight=0, colour=0.
+ * Sharding: the grid is cut into x-sheets one brick (8 voxels) thick; sheet s belongs to rank
+ * s % world.  rank=0, world=1 gives the whole grid.  No per-frame communication is needed. */
+int tsdf_grid_create(const int64_t dim[3], const float origin[3], double voxel_size, double trunc,
+                     int device, int rank, int world, tsdf_grid **out);
+int tsdf_grid_destroy(tsdf_grid *g);
+
+/* TSDFVolume.integrate (grid_fusion.py:214-314, CPU branch semantics) -- HOST frame buffers. */
+int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const double *depth, int H, int W,
+                        const double K[9], const double Tinv[16], double obs_weight);
+/* Same, frame already resident in device memory (throughput runs; no H2D inside). */
+int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W,
+                               const double K[9], const double Tinv[16], double obs_weight);
+
+/* TSDFVolume.get_volume (grid_fusion.py:316-320) plus the weight plane (_weight_vol_cpu).
+ * Writes this rank's sheets, un-bricked, as C-order [nx_local][Y][Z] float32 host arrays; any
+ * pointer may be NULL.  nx_local and the global x index of every local row come from
+ * tsdf_grid_local_x(). */
+int tsdf_grid_download(tsdf_grid *g, float *tsdf, float *weight, float *color);
+/* Same into DEVICE buffers (for the NCCL gather done by the caller's torch.distributed). */
+int tsdf_grid_download_device(tsdf_grid *g, float *d_tsdf, float *d_weight, float *d_color);
+/* n_x: number of local x rows (voxels).  xs (may be NULL): their global x indices, ascending. */
+int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs);
+
+/* counters[0] voxels updated by the last frame, [1] voxels updated since create,
+ * [2] bricks visited by the last frame, [3] frames integrated. */
+int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4]);
+int tsdf_grid_sync(tsdf_grid *g);
+/* Milliseconds the device spent on the last integrate call's kernels (CUDA events on the
+ * handle's stream; waits for them). */
+int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel-block hash map.  Replaces hash_fusion.HashTable (hash_fusion.py:29-507) on the
+ * integrate / get_volume path.  Storage is 8^3-voxel blocks found through a lock-free
+ * open-addressing table keyed on packed 64-bit block coordinates (hash: hash_fusion.py:182-190
+ * primes), block storage from an atomic free-list heap.  A block exists iff at least one of its
+ * voxels has been updated, so {exported blocks} == {v // 8 : the reference map has an entry v}.
+ * --------------------------------------------------------------------------------------------- */
+
+/* HashTable.__init__ (hash_fusion.py:34-69).  table_slots: open-addressing capacity (rounded up
+ * to a power of two); heap_blocks: voxel-block capacity of this rank.  Sharding: a block belongs
+ * to rank owner(key) % world (owner hash decorrelated from the slot hash). */
+int vh_create(const int64_t dim[3], const float origin[3], double voxel_size, double trunc,
+              int64_t table_slots, int64_t heap_blocks, int device, int rank, int world,
+              tsdf_hash **out);
+int vh_destroy(tsdf_hash *h);
+
+/* HashTable.integrate (hash_fusion.py:103-145).  obs_weight follows the dense rule. */
+int vh_integrate(tsdf_hash *h, const uint8_t *rgb, const double *depth, int H, int W,
+                 const double K[9], const double Tinv[16], double obs_weight);
+int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,
+                        const double K[9], const double Tinv[16], double obs_weight);
+
+/* HashTable.count_num_hash_entries / get_load_factor / get_num_collisions analogues
+ * (hash_fusion.py:147-180).  stats[0] allocated blocks, [1] table keys (incl. keys whose block
+ * never received an update), [2] table slots, [3] heap capacity, [4] free heap blocks,
+ * [5] voxels updated by the last frame, [6] voxels updated since create, [7] blocks visited by
+ * the last frame, [8] longest probe sequence seen, [9] keys inserted by the last frame,
+ * [10] frames integrated, [11] candidate keys emitted by the last frame's ray walk. */
+int vh_stats(tsdf_hash *h, int64_t stats[12]);
+int vh_num_blocks(tsdf_hash *h, int64_t *n);
+
+/* Block export: keys[n][3] int32 block coordinates (voxel // 8), payload[n][1536] float32
+ * (tsdf | weight | colour, voxel order x*64 + y*8 + z inside the block).  Call with NULL
+ * pointers to get n only.  Order is unspecified (compare as a set). */
+int vh_export_blocks(tsdf_hash *h, int64_t capacity, int64_t *n, int32_t *keys, float *payload);
+
+/* HashTable.get_volume (hash_fusion.py:442-463): scatter into dense C-order [X][Y][Z] float32
+ * volumes (tsdf default 1, weight 0, colour 0).  Host pointers, any may be NULL.  With world > 1
+ * each rank writes only its own blocks; the caller merges (blocks are disjoint). */
+int vh_to_dense(tsdf_hash *h, float *tsdf, float *weight, float *color);
+int vh_to_dense_device(tsdf_hash *h, float *d_tsdf, float *d_weight, float *d_color);
+
+/* Free every block whose key is listed (keys[n][3]); their storage returns to the heap.
+ * Mirrors HashTable.remove (hash_fusion.py:322-393) at block granularity. */
+int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, int64_t *removed);
+int vh_sync(tsdf_hash *h);
+int vh_last_kernel_ms(tsdf_hash *h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_B200_H */

@@ -1,0 +1,501 @@
+// capi_grid.cu -- C ABI of the dense brick grid (include/tsdf_b200.h, tsdf_grid_*) and the host
+// plumbing shared with the hash map (errors, frame constants, frame upload).
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "host_common.h"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void tsdf_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *tsdf_last_error(void) { return g_err; }
+
+extern "C" int tsdf_device_info(int device, int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        tsdf_set_error("no CUDA device available (this library has no CPU fallback)");
+        return TSDF_ERR_NO_DEVICE;
+    }
+    BAD_ARG(device < 0 || device >= n, "device %d out of range (%d devices)", device, n);
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return TSDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int VolumeGeom::init(const int64_t dim_[3], const float origin_[3], double vs_, double trunc_)
+{
+    BAD_ARG(!dim_ || !origin_, "dim/origin is NULL");
+    BAD_ARG(!(vs_ > 0.0) || !(trunc_ > 0.0), "voxel_size and trunc must be positive");
+    int total_pad = 0;
+    max_abs_coord = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        BAD_ARG(dim_[a] <= 0 || dim_[a] > (1 << 20), "dim[%d]=%lld out of range", a, (long long)dim_[a]);
+        dim[a] = dim_[a];
+        origin[a] = origin_[a];
+        nb[a] = (int)((dim_[a] + BRICK - 1) / BRICK);
+        lat_off[a] = total_pad;
+        total_pad += nb[a] * BRICK;
+    }
+    vs = vs_;
+    trunc = trunc_;
+    // grid_fusion.py:175-180: cam_pts = f32( f64(f32 origin) + vs * f64(f32(idx)) ), later upcast to f64
+    std::vector<double> lat((size_t)total_pad);
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < nb[a] * BRICK; ++i) {
+            volatile double prod = vs * (double)(float)i; // volatile: keep mul and add separately rounded
+            const float w = (float)((double)origin[a] + prod);
+            lat[(size_t)lat_off[a] + i] = (double)w;
+            if (i < dim[a]) max_abs_coord = std::max(max_abs_coord, fabs((double)w));
+        }
+    CUDA_TRY(cudaMalloc(&d_lat, lat.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(d_lat, lat.data(), lat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return TSDF_OK;
+}
+
+void VolumeGeom::release()
+{
+    if (d_lat) cudaFree(d_lat);
+    d_lat = nullptr;
+}
+
+VolumeParams VolumeGeom::params() const
+{
+    VolumeParams v;
+    v.lat_x = d_lat + lat_off[0];
+    v.lat_y = d_lat + lat_off[1];
+    v.lat_z = d_lat + lat_off[2];
+    v.dim_x = (int)dim[0]; v.dim_y = (int)dim[1]; v.dim_z = (int)dim[2];
+    v.nbx = nb[0]; v.nby = nb[1]; v.nbz = nb[2];
+    return v;
+}
+
+double VolumeGeom::brick_radius() const
+{
+    // centres span 7 voxels per axis -> half diagonal 3.5*sqrt(3)*vs; the lattice itself is
+    // float32-rounded (<= 2^-24 relative per axis), covered by the second term
+    return 3.5 * 1.7320508075688772 * vs * 1.0001 + ldexp(max_abs_coord + 1.0, -21);
+}
+
+int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
+                      const double Tinv[16], double obs)
+{
+    BAD_ARG(!K || !Tinv, "K/Tinv is NULL");
+    BAD_ARG(H <= 0 || W <= 0 || H > 4095 || W > 4095, "image size %dx%d unsupported (1..4095)", W, H);
+    BAD_ARG(!(obs > 0.0) || !isfinite(obs), "obs_weight must be a positive finite number");
+    for (int i = 0; i < 12; ++i) {
+        BAD_ARG(!isfinite(Tinv[i]), "Tinv has a non-finite entry");
+        f->T[i] = Tinv[i];
+    }
+    // grid_fusion.py:190-192: intrinsics are cast to float32 before use
+    f->fx = (double)(float)K[0];
+    f->fy = (double)(float)K[4];
+    f->cx = (double)(float)K[2];
+    f->cy = (double)(float)K[5];
+    BAD_ARG(!isfinite(f->fx) || !isfinite(f->fy) || !(fabs(f->cx) <= 8192.0) || !(fabs(f->cy) <= 8192.0),
+            "intrinsics out of range");
+    f->trunc = g.trunc;
+    f->neg_trunc = -g.trunc;
+    f->obs = obs;
+    f->obs_f = (float)obs;
+    f->H = H;
+    f->W = W;
+    f->depth = nullptr;
+    f->cfold = nullptr;
+    for (int r = 0; r < 3; ++r)
+        c->Tn[r] = sqrt(Tinv[4 * r] * Tinv[4 * r] + Tinv[4 * r + 1] * Tinv[4 * r + 1] + Tinv[4 * r + 2] * Tinv[4 * r + 2]) * 1.0000001;
+    c->max_depth = 0.0;
+    c->rho = g.brick_radius();
+    c->vs = g.vs;
+    c->ox = (double)g.origin[0];
+    c->oy = (double)g.origin[1];
+    c->oz = (double)g.origin[2];
+    return TSDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int FrameIO::init()
+{
+    CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreate(&k_begin));
+    CUDA_TRY(cudaEventCreate(&k_end));
+    return TSDF_OK;
+}
+
+int FrameIO::ensure_cfold(int npix)
+{
+    if (npix <= cap_pix && d_cfold) return TSDF_OK;
+    return ensure(npix);
+}
+
+int FrameIO::ensure(int npix)
+{
+    if (npix <= cap_pix) return TSDF_OK;
+    CUDA_TRY(cudaStreamSynchronize(compute));
+    CUDA_TRY(cudaStreamSynchronize(copy));
+    for (int i = 0; i < 2; ++i) {
+        if (d_rgb[i]) cudaFree(d_rgb[i]);
+        if (d_depth[i]) cudaFree(d_depth[i]);
+        if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
+        if (h_depth[i]) cudaFreeHost(h_depth[i]);
+        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr;
+    }
+    if (d_cfold) cudaFree(d_cfold);
+    d_cfold = nullptr;
+    cap_pix = 0;
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&d_rgb[i], (size_t)npix * 3));
+        CUDA_TRY(cudaMalloc(&d_depth[i], (size_t)npix * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
+        CUDA_TRY(cudaMallocHost(&h_depth[i], (size_t)npix * sizeof(double)));
+    }
+    CUDA_TRY(cudaMalloc(&d_cfold, (size_t)npix * sizeof(uint32_t)));
+    cap_pix = npix;
+    return TSDF_OK;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uint8_t **d_rgb_out,
+                    const double **d_depth_out)
+{
+    int rc = ensure(npix);
+    if (rc) return rc;
+    const int s = next;
+    next ^= 1;
+    const bool pinned = is_pinned_host(rgb) && is_pinned_host(depth);
+    const uint8_t *src_rgb = rgb;
+    const double *src_depth = depth;
+    if (!pinned) {
+        // the staging slot was last read by the H2D copy issued two frames ago
+        CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+        memcpy(h_rgb[s], rgb, (size_t)npix * 3);
+        memcpy(h_depth[s], depth, (size_t)npix * sizeof(double));
+        src_rgb = h_rgb[s];
+        src_depth = h_depth[s];
+    }
+    // the device slot was last read by the kernels of the frame two calls ago
+    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
+    CUDA_TRY(cudaMemcpyAsync(d_depth[s], src_depth, (size_t)npix * sizeof(double), cudaMemcpyHostToDevice, copy));
+    CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
+    CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
+    CUDA_TRY(cudaStreamWaitEvent(compute, h2d_done[s], 0));
+    // the caller's buffers are only borrowed for the duration of the call
+    if (pinned) CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+    cur = s;
+    *d_rgb_out = d_rgb[s];
+    *d_depth_out = d_depth[s];
+    return TSDF_OK;
+}
+
+int FrameIO::begin_kernels()
+{
+    CUDA_TRY(cudaEventRecord(k_begin, compute));
+    return TSDF_OK;
+}
+
+int FrameIO::end_kernels()
+{
+    CUDA_TRY(cudaEventRecord(k_end, compute));
+    timed = true;
+    if (cur >= 0) {
+        CUDA_TRY(cudaEventRecord(slot_free[cur], compute));
+        cur = -1;
+    }
+    return TSDF_OK;
+}
+
+int FrameIO::last_ms(float *ms)
+{
+    BAD_ARG(!ms, "ms is NULL");
+    BAD_ARG(!timed, "no frame integrated yet");
+    CUDA_TRY(cudaEventSynchronize(k_end));
+    CUDA_TRY(cudaEventElapsedTime(ms, k_begin, k_end));
+    return TSDF_OK;
+}
+
+void FrameIO::release()
+{
+    if (compute) cudaStreamSynchronize(compute);
+    if (copy) cudaStreamSynchronize(copy);
+    for (int i = 0; i < 2; ++i) {
+        if (d_rgb[i]) cudaFree(d_rgb[i]);
+        if (d_depth[i]) cudaFree(d_depth[i]);
+        if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
+        if (h_depth[i]) cudaFreeHost(h_depth[i]);
+        if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
+        if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    }
+    if (d_cfold) cudaFree(d_cfold);
+    if (k_begin) cudaEventDestroy(k_begin);
+    if (k_end) cudaEventDestroy(k_end);
+    if (compute) cudaStreamDestroy(compute);
+    if (copy) cudaStreamDestroy(copy);
+}
+
+int tsdf_select_device(int device, int *sm_count)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        tsdf_set_error("no CUDA device available (this library has no CPU fallback)");
+        return TSDF_ERR_NO_DEVICE;
+    }
+    BAD_ARG(device < 0 || device >= n, "device %d out of range (%d devices)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) {
+        tsdf_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+        return TSDF_ERR_NO_DEVICE;
+    }
+    *sm_count = p.multiProcessorCount;
+    return TSDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct tsdf_grid {
+    int device = 0, sm_count = 0, rank = 0, world = 1;
+    VolumeGeom geom;
+    FrameIO io;
+    int nlbx = 0;              // local brick sheets
+    int64_t n_x_local = 0;     // local voxel rows
+    size_t nbricks = 0;
+    float *bricks = nullptr;
+    BrickRef *vis_list = nullptr;
+    FrameScratch *fs = nullptr;
+    Totals *tot = nullptr;
+    int integrate_grid = 0;
+    int64_t frames = 0;
+};
+
+static int grid_free(tsdf_grid *g)
+{
+    if (!g) return TSDF_OK;
+    cudaSetDevice(g->device);
+    g->io.release();
+    g->geom.release();
+    if (g->bricks) cudaFree(g->bricks);
+    if (g->vis_list) cudaFree(g->vis_list);
+    if (g->fs) cudaFree(g->fs);
+    if (g->tot) cudaFree(g->tot);
+    delete g;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], double voxel_size, double trunc,
+                                int device, int rank, int world, tsdf_grid **out)
+{
+    BAD_ARG(!out, "out is NULL");
+    *out = nullptr;
+    BAD_ARG(world < 1 || rank < 0 || rank >= world, "bad rank/world %d/%d", rank, world);
+    int sm = 0;
+    int rc = tsdf_select_device(device, &sm);
+    if (rc) return rc;
+    tsdf_grid *g = new (std::nothrow) tsdf_grid;
+    BAD_ARG(!g, "out of host memory");
+    g->device = device;
+    g->sm_count = sm;
+    g->rank = rank;
+    g->world = world;
+    if ((rc = g->geom.init(dim, origin, voxel_size, trunc)) || (rc = g->io.init())) {
+        grid_free(g);
+        return rc;
+    }
+    const int nbx = g->geom.nb[0];
+    g->nlbx = nbx > rank ? (nbx - rank + world - 1) / world : 0;
+    g->n_x_local = 0;
+    for (int l = 0; l < g->nlbx; ++l) {
+        const int64_t x0 = (int64_t)(l * world + rank) * BRICK;
+        g->n_x_local += std::min<int64_t>(BRICK, dim[0] - x0);
+    }
+    g->nbricks = (size_t)g->nlbx * g->geom.nb[1] * g->geom.nb[2];
+    if (g->nbricks >= (size_t)1 << 31) {
+        grid_free(g);
+        tsdf_set_error("too many bricks per rank (%zu)", g->nbricks);
+        return TSDF_ERR_BAD_ARG;
+    }
+    cudaError_t e;
+    const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
+    if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list, nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->fs, sizeof(FrameScratch))) != cudaSuccess ||
+        (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
+        tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
+        cudaGetLastError();
+        grid_free(g);
+        return TSDF_ERR_OOM;
+    }
+    cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), g->io.compute);
+    cudaMemsetAsync(g->tot, 0, sizeof(Totals), g->io.compute);
+    launch_fill_bricks(g->bricks, g->nbricks, sm, g->io.compute);
+    g->integrate_grid = sm * integrate_dense_ctas_per_sm();
+    e = cudaStreamSynchronize(g->io.compute);
+    if (e != cudaSuccess) {
+        tsdf_set_error("grid initialisation failed: %s", cudaGetErrorString(e));
+        grid_free(g);
+        return TSDF_ERR_CUDA;
+    }
+    *out = g;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_destroy(tsdf_grid *g) { return grid_free(g); }
+
+static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
+                    CullParams &c)
+{
+    int rc = g->io.ensure_cfold(H * W);
+    if (rc) return rc;
+    cudaStream_t s = g->io.compute;
+    f.depth = d_depth;
+    f.cfold = g->io.d_cfold;
+    if ((rc = g->io.begin_kernels())) return rc;
+    CUDA_TRY(cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), s));
+    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->fs, H * W, g->sm_count, s);
+    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->vis_list, g->fs, s);
+    launch_integrate_dense(f, g->geom.params(), g->vis_list, g->bricks, g->fs, g->tot, g->integrate_grid, s);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = g->io.end_kernels())) return rc;
+    g->frames++;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const double *depth, int H, int W,
+                                   const double K[9], const double Tinv[16], double obs_weight)
+{
+    BAD_ARG(!g || !rgb || !depth, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const uint8_t *d_rgb;
+    const double *d_depth;
+    if ((rc = g->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
+    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+}
+
+extern "C" int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W,
+                                          const double K[9], const double Tinv[16], double obs_weight)
+{
+    BAD_ARG(!g || !d_rgb || !d_depth, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+}
+
+extern "C" int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs)
+{
+    BAD_ARG(!g, "NULL handle");
+    if (n_x) *n_x = g->n_x_local;
+    if (xs) {
+        int64_t k = 0;
+        for (int l = 0; l < g->nlbx; ++l) {
+            const int64_t x0 = (int64_t)(l * g->world + g->rank) * BRICK;
+            for (int64_t x = x0; x < std::min<int64_t>(x0 + BRICK, g->geom.dim[0]); ++x) xs[k++] = x;
+        }
+    }
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_download_device(tsdf_grid *g, float *d_tsdf, float *d_weight, float *d_color)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    launch_unbrick(g->bricks, (int)g->n_x_local, (int)g->geom.dim[1], (int)g->geom.dim[2], g->geom.nb[1],
+                   g->geom.nb[2], d_tsdf, d_weight, d_color, g->sm_count, g->io.compute);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(g->io.compute));
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_download(tsdf_grid *g, float *tsdf, float *weight, float *color)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t n = (size_t)g->n_x_local * g->geom.dim[1] * g->geom.dim[2];
+    if (!n) return TSDF_OK;
+    // one plane at a time keeps the device-side scratch at 4 B/voxel
+    float *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, n * sizeof(float)));
+    float *host[3] = {tsdf, weight, color};
+    for (int p = 0; p < 3; ++p) {
+        if (!host[p]) continue;
+        launch_unbrick(g->bricks, (int)g->n_x_local, (int)g->geom.dim[1], (int)g->geom.dim[2], g->geom.nb[1],
+                       g->geom.nb[2], p == 0 ? scratch : nullptr, p == 1 ? scratch : nullptr,
+                       p == 2 ? scratch : nullptr, g->sm_count, g->io.compute);
+        cudaError_t e = cudaMemcpyAsync(host[p], scratch, n * sizeof(float), cudaMemcpyDeviceToHost, g->io.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->io.compute);
+        if (e != cudaSuccess) {
+            cudaFree(scratch);
+            tsdf_set_error("download failed: %s", cudaGetErrorString(e));
+            return TSDF_ERR_CUDA;
+        }
+    }
+    cudaFree(scratch);
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
+{
+    BAD_ARG(!g || !counters, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaStreamSynchronize(g->io.compute));
+    FrameScratch fs;
+    Totals tot;
+    CUDA_TRY(cudaMemcpy(&fs, g->fs, sizeof(fs), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&tot, g->tot, sizeof(tot), cudaMemcpyDeviceToHost));
+    counters[0] = (int64_t)fs.updated;
+    counters[1] = (int64_t)tot.updated;
+    counters[2] = (int64_t)tot.last_visited;
+    counters[3] = g->frames;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_sync(tsdf_grid *g)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaStreamSynchronize(g->io.copy));
+    CUDA_TRY(cudaStreamSynchronize(g->io.compute));
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    return g->io.last_ms(ms);
+}

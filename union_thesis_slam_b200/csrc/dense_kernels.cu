@@ -1,0 +1,179 @@
+// dense_kernels.cu -- sm_100a kernels of the dense brick grid (K1 of SURVEY.md section 2a).
+//
+// Data layout in HBM: the grid is stored as 8x8x8-voxel bricks, one 6 KB record per brick:
+//   record = [512 tsdf | 512 weight | 512 colour] float32, voxel order (x*8 + y)*8 + z.
+// A z-run of 8 voxels is one 32 B sector per plane; a warp's float4 accesses cover 512 B
+// contiguous, so every DRAM transaction is a full sector and bricks the frame cannot touch are
+// never read.  Brick (bx,by,bz) of this rank lives at index ((bx/world)*nby + by)*nbz + bz.
+//
+// Per frame:  prep_frame (fold colour, max depth)  ->  cull_bricks (frustum + depth range,
+// warp-aggregated compaction)  ->  integrate_bricks (persistent CTAs over the visible list).
+#include "launch.h"
+#include "tsdf_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill_bricks(float4 *bricks, size_t n_float4)
+{
+    // record pattern: first 128 float4 of every 384 are tsdf = 1, the rest 0
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_float4; i += stride) {
+        const float v = (i % 384) < 128 ? 1.0f : 0.0f;
+        bricks[i] = make_float4(v, v, v, v);
+    }
+}
+
+// grid_fusion.py:228-232 colour fold (as an exact integer) + max valid depth of the frame.
+__global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__restrict__ depth,
+                             uint32_t *__restrict__ cfold, FrameScratch *fs, int npix)
+{
+    float m = 0.0f;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const uint32_t r = rgb[3 * p], g = rgb[3 * p + 1], b = rgb[3 * p + 2];
+        cfold[p] = (b << 16) | (g << 8) | r;
+        const double d = depth[p];
+        if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&fs->max_depth_bits, __float_as_uint(m));
+}
+
+// One thread per local brick; visible bricks are appended with one atomic per warp.
+__global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, int nbz, int rank, int world,
+                              BrickRef *__restrict__ list, FrameScratch *fs)
+{
+    const int n = nlbx * nby * nbz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool vis = false;
+    int bx = 0, by = 0, bz = 0;
+    if (i < n) {
+        bz = i % nbz;
+        by = (i / nbz) % nby;
+        bx = (i / (nbz * nby)) * world + rank;
+        c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+        vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, vis);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&fs->vis_count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (vis) {
+        BrickRef r;
+        r.bx = bx; r.by = by; r.bz = bz; r.storage = (uint32_t)i;
+        list[base + __popc(ballot & ((1u << lane) - 1u))] = r;
+    }
+}
+
+// Persistent CTAs; one brick per iteration, thread t owns voxels (x = t>>4, y = (t>>1)&7,
+// z = 4*(t&1) .. +3): one float4 per plane.  Geometry first (float64, no voxel traffic), then
+// only threads with at least one passing voxel read-modify-write their 3 x 16 B.
+__global__ void __launch_bounds__(INTEGRATE_THREADS, 6)
+k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
+                  FrameScratch *fs, Totals *tot)
+{
+    const int n = fs->vis_count;
+    const int t = threadIdx.x;
+    const int lx = t >> 4, ly = (t >> 1) & 7, lz0 = (t & 1) * 4;
+    unsigned my_updates = 0;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int4 br = __ldg(reinterpret_cast<const int4 *>(list) + b);
+        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly, gz0 = br.z * BRICK + lz0;
+        if (gx >= v.dim_x || gy >= v.dim_y || gz0 >= v.dim_z) continue;
+        const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
+        const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
+        const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
+        const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
+        const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0));
+        const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0) + 1);
+        const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
+        double dist[4];
+        int pix[4];
+        unsigned mask = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (gz0 + e < v.dim_z && project_voxel(f, cX, cY, cZ, wz[e], dist[e], pix[e])) mask |= 1u << e;
+        if (!mask) continue;
+        float *rec = bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 4 * t;
+        float4 T4 = *reinterpret_cast<float4 *>(rec);
+        float4 W4 = *reinterpret_cast<float4 *>(rec + BRICK_VOX);
+        float4 C4 = *reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX);
+        if (mask & 1u) update_voxel(f, T4.x, W4.x, C4.x, dist[0], pix[0]);
+        if (mask & 2u) update_voxel(f, T4.y, W4.y, C4.y, dist[1], pix[1]);
+        if (mask & 4u) update_voxel(f, T4.z, W4.z, C4.z, dist[2], pix[2]);
+        if (mask & 8u) update_voxel(f, T4.w, W4.w, C4.w, dist[3], pix[3]);
+        *reinterpret_cast<float4 *>(rec) = T4;
+        *reinterpret_cast<float4 *>(rec + BRICK_VOX) = W4;
+        *reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX) = C4;
+        my_updates += __popc(mask);
+    }
+    for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
+    if ((t & 31) == 0 && my_updates) {
+        atomicAdd(&fs->updated, (unsigned long long)my_updates);
+        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    }
+    if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
+}
+
+// Read-out: bricks -> C-order [n_x][Y][Z] planes (grid_fusion.py:316-320 layout).
+__global__ void k_unbrick(const float *__restrict__ bricks, int n_x, int dim_y, int dim_z, int nby, int nbz,
+                          float *__restrict__ tsdf, float *__restrict__ wgt, float *__restrict__ col)
+{
+    const size_t total = (size_t)n_x * dim_y * dim_z;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const int k = (int)(o % dim_z);
+        const int j = (int)((o / dim_z) % dim_y);
+        const int i = (int)(o / ((size_t)dim_z * dim_y));
+        const size_t brick = ((size_t)(i >> 3) * nby + (j >> 3)) * nbz + (k >> 3);
+        const float *rec = bricks + brick * BRICK_FLOATS + ((i & 7) * 64 + (j & 7) * 8 + (k & 7));
+        if (tsdf) tsdf[o] = __ldg(rec);
+        if (wgt) wgt[o] = __ldg(rec + BRICK_VOX);
+        if (col) col[o] = __ldg(rec + 2 * BRICK_VOX);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (declared in launch.h)
+void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_t s)
+{
+    const size_t n4 = nbricks * (BRICK_FLOATS / 4);
+    if (!n4) return;
+    k_fill_bricks<<<sm_count * 8, 256, 0, s>>>(reinterpret_cast<float4 *>(bricks), n4);
+}
+
+void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs, int npix,
+                       int sm_count, cudaStream_t s)
+{
+    int blocks = (npix + 255) / 256;
+    if (blocks > sm_count * 8) blocks = sm_count * 8;
+    k_prep_frame<<<blocks, 256, 0, s>>>(rgb, depth, cfold, fs, npix);
+}
+
+void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
+                        BrickRef *list, FrameScratch *fs, cudaStream_t s)
+{
+    const long long n = (long long)nlbx * nby * nbz;
+    if (!n) return;
+    k_cull_bricks<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, list, fs);
+}
+
+int integrate_dense_ctas_per_sm()
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense, INTEGRATE_THREADS, 0);
+    return n > 0 ? n : 1;
+}
+
+void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
+                            FrameScratch *fs, Totals *tot, int grid, cudaStream_t s)
+{
+    k_integrate_dense<<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
+}
+
+void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
+                    float *col, int sm_count, cudaStream_t s)
+{
+    if (!n_x) return;
+    k_unbrick<<<sm_count * 16, 256, 0, s>>>(bricks, n_x, dim_y, dim_z, nby, nbz, tsdf, wgt, col);
+}

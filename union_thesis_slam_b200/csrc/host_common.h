@@ -1,0 +1,81 @@
+// host_common.h -- host-side plumbing shared by the dense-grid and hash-map C ABI:
+// error reporting, per-frame constants, and the double-buffered host->device frame path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tsdf_b200.h"
+#include "launch.h"
+#include "tsdf_common.cuh"
+
+void tsdf_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            tsdf_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? TSDF_ERR_OOM : TSDF_ERR_CUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+#define BAD_ARG(cond, ...)                \
+    do {                                  \
+        if (cond) {                       \
+            tsdf_set_error(__VA_ARGS__);  \
+            return TSDF_ERR_BAD_ARG;      \
+        }                                 \
+    } while (0)
+
+// Geometry common to both maps (grid_fusion.py:33-44 / hash_fusion.py:42-53).
+struct VolumeGeom {
+    int64_t dim[3];
+    float origin[3];
+    double vs, trunc;
+    int nb[3];           // bricks per axis (global)
+    double *d_lat = nullptr; // device: lat_x | lat_y | lat_z, each padded to a multiple of 8
+    int lat_off[3];
+    double max_abs_coord;
+
+    int init(const int64_t dim_[3], const float origin_[3], double vs_, double trunc_);
+    void release();
+    VolumeParams params() const;
+    // world-space radius that covers every voxel centre of a brick around the brick centre
+    double brick_radius() const;
+};
+
+int tsdf_select_device(int device, int *sm_count);
+int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
+                      const double Tinv[16], double obs);
+
+// Double-buffered frame upload.  Host frames go through pinned staging (or straight from the
+// caller's buffer when that is already pinned) on a copy stream; kernels of frame n overlap the
+// upload of frame n+1.
+struct FrameIO {
+    cudaStream_t compute = nullptr, copy = nullptr;
+    int cap_pix = 0;
+    uint8_t *d_rgb[2] = {nullptr, nullptr};
+    double *d_depth[2] = {nullptr, nullptr};
+    uint8_t *h_rgb[2] = {nullptr, nullptr};
+    double *h_depth[2] = {nullptr, nullptr};
+    uint32_t *d_cfold = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
+    cudaEvent_t k_begin = nullptr, k_end = nullptr;
+    int next = 0, cur = -1;
+    bool timed = false;
+
+    int init();
+    int ensure(int npix);
+    // stages the frame and makes `compute` wait for it; returns device pointers of the slot
+    int upload(const uint8_t *rgb, const double *depth, int npix, const uint8_t **d_rgb_out,
+               const double **d_depth_out);
+    int ensure_cfold(int npix);
+    int begin_kernels();
+    int end_kernels(); // records timing + releases the upload slot
+    int last_ms(float *ms);
+    void release();
+};

@@ -1,0 +1,187 @@
+"""Voxel-block hash map TSDF fusion on B200 -- drop-in for the reference's ``hash_fusion`` module
+on the integrate / get_volume path.
+
+The reference ``HashTable`` (hash_fusion.py:29-507) is a Python list of 5-slot buckets holding one
+entry per *voxel*.  Here the map stores 8^3-voxel blocks in HBM, found through a lock-free
+open-addressing table keyed on packed 64-bit block coordinates (same three primes as
+hash_fusion.py:24-26), with block storage from an atomic free-list heap; per frame a ray walk
+emits candidate blocks, new keys are inserted with atomicCAS, visible blocks are compacted and
+each is integrated by one CTA (csrc/hash_kernels.cu).  A block exists iff one of its voxels was
+updated, so the exported block set equals {v // 8 : v is an entry of the reference map}.
+
+Voxel arithmetic is the dense rule (float32 state, reference grid_fusion.py:207-211,302-314):
+dense and hash outputs are then identical, and differ from the reference hash map's float64
+running mean (voxel.py:32-37) by ~1e-7 in tsdf only.  ``obs_weight`` is honoured (the reference
+silently drops it, hash_fusion.py:141,145; pass 1.0 to compare).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, dist
+
+P1 = 73856093
+P2 = 19349669
+P3 = 83492791
+BLOCK = 8
+
+
+class HashTable:
+    """The data structure for voxel storage and retrieval: hash tables (reference hash_fusion.py:29)."""
+
+    def __init__(self, vol_bounds, voxel_size, map_size=1000000, load_factor=0.75, use_gpu=False,
+                 heap_blocks=None, rank=None, world_size=None, device=None, group=None):
+        """``map_size`` is the number of table slots (reference: number of buckets,
+        hash_fusion.py:36).  ``heap_blocks`` (extension) bounds the number of 8^3 blocks this rank
+        can hold; default: every block of the bounded volume, capped at map_size."""
+        vol_bounds = np.asarray(vol_bounds)
+        assert vol_bounds.shape == (3, 2), "[!] `vol_bounds` should be of shape (3, 2)."
+        self._vol_bounds = vol_bounds
+        self._voxel_size = voxel_size
+        self._trunc_margin = 5 * self._voxel_size
+        self._color_const = 256 * 256
+        self._load_factor = 0.75  # the reference ignores its argument too (hash_fusion.py:38)
+        self._bucket_size = 1
+        # hash_fusion.py:50-57, including the in-place snap of the caller's upper bounds
+        self._vol_dim = np.ceil((self._vol_bounds[:, 1] - self._vol_bounds[:, 0]) / self._voxel_size).copy(
+            order='C').astype(int)
+        self._vol_bounds[:, 1] = self._vol_bounds[:, 0] + self._vol_dim * self._voxel_size
+        self._vol_origin = self._vol_bounds[:, 0].copy(order='C').astype(np.float32)
+        print("Voxel volume size: {} x {} x {} - # points: {:,}".format(
+            self._vol_dim[0], self._vol_dim[1], self._vol_dim[2],
+            self._vol_dim[0] * self._vol_dim[1] * self._vol_dim[2]))
+
+        self.rank, self.world_size = dist.rank_world(rank, world_size)
+        self.device = dist.local_device(device)
+        self._group = group
+        nblocks_total = int(np.prod((self._vol_dim + BLOCK - 1) // BLOCK))
+        if heap_blocks is None:
+            heap_blocks = min(nblocks_total, int(map_size))
+        self._lib = _capi.lib()
+        self._handle = C.c_void_p()
+        dim = np.ascontiguousarray(self._vol_dim, dtype=np.int64)
+        _capi.check(self._lib.vh_create(
+            _capi.ptr(dim), _capi.ptr(self._vol_origin), float(self._voxel_size), float(self._trunc_margin),
+            int(map_size), int(heap_blocks), self.device, self.rank, self.world_size, C.byref(self._handle)))
+        self._table_size = self.stats()["table_slots"]
+
+    # -- hot path ------------------------------------------------------------------------------
+    def integrate(self, color_im, depth_im, cam_intr, cam_pose, obs_weight=1.):
+        """Integrate an RGB-D image into the hash map (reference hash_fusion.py:103-145)."""
+        im_h, im_w = depth_im.shape
+        rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth_im, dtype=np.float64)
+        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
+        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))  # hash_fusion.py:112
+        _capi.check(self._lib.vh_integrate(
+            self._handle, _capi.ptr(rgb), _capi.ptr(depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            float(obs_weight)))
+
+    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
+        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
+        tinv = np.ascontiguousarray(tinv, dtype=np.float64)
+        _capi.check(self._lib.vh_integrate_device(
+            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            float(obs_weight)))
+
+    # -- read-out ------------------------------------------------------------------------------
+    def get_volume_with_weight(self):
+        """(tsdf, weight, color) dense float32 [X,Y,Z]; with world_size > 1 the union over ranks."""
+        shape = tuple(int(d) for d in self._vol_dim)
+        if self.world_size == 1:
+            t = np.empty(shape, np.float32)
+            w = np.empty(shape, np.float32)
+            c = np.empty(shape, np.float32)
+            _capi.check(self._lib.vh_to_dense(self._handle, _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
+            return t, w, c
+        import torch
+        dev = torch.device("cuda", self.device)
+        t = torch.empty(shape, dtype=torch.float32, device=dev)
+        w = torch.empty(shape, dtype=torch.float32, device=dev)
+        c = torch.empty(shape, dtype=torch.float32, device=dev)
+        _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
+        t, w, c = dist.merge_disjoint_volumes(t, w, c, self._group)
+        return t.cpu().numpy(), w.cpu().numpy(), c.cpu().numpy()
+
+    def get_volume(self):
+        """tsdf (default 1) and colour (default 0) volumes (reference hash_fusion.py:442-463)."""
+        t, _, c = self.get_volume_with_weight()
+        return t, c
+
+    def export_blocks(self):
+        """This rank's blocks: keys (n,3) int32 (voxel // 8), payload (n,3,8,8,8) float32
+        [tsdf|weight|colour][x][y][z]."""
+        n = C.c_int64()
+        _capi.check(self._lib.vh_export_blocks(self._handle, 0, C.byref(n), None, None))
+        keys = np.empty((n.value, 3), np.int32)
+        payload = np.empty((n.value, 3, BLOCK, BLOCK, BLOCK), np.float32)
+        _capi.check(self._lib.vh_export_blocks(self._handle, n.value, C.byref(n), _capi.ptr(keys),
+                                               _capi.ptr(payload)))
+        return keys[:n.value], payload[:n.value]
+
+    def remove_blocks(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.int32).reshape(-1, 3)
+        removed = C.c_int64()
+        _capi.check(self._lib.vh_remove_blocks(self._handle, _capi.ptr(keys), len(keys), C.byref(removed)))
+        return removed.value
+
+    # -- occupancy metrics (reference hash_fusion.py:147-180) ------------------------------------
+    def stats(self):
+        s = np.zeros(12, np.int64)
+        _capi.check(self._lib.vh_stats(self._handle, _capi.ptr(s)))
+        names = ["blocks", "table_keys", "table_slots", "heap_capacity", "heap_free", "updated_last",
+                 "updated_total", "blocks_visited_last", "max_probe", "keys_inserted_last", "frames",
+                 "candidates_last"]
+        return {k: int(v) for k, v in zip(names, s)}
+
+    def count_num_hash_entries(self):
+        """Number of stored entries; here an entry is an allocated 8^3 block."""
+        return self.stats()["blocks"]
+
+    def get_num_non_empty_bucket(self):
+        return self.stats()["table_keys"]
+
+    get_num_non_empty_buckets = get_num_non_empty_bucket
+
+    def get_load_factor(self):
+        s = self.stats()
+        return s["table_keys"] / s["table_slots"]
+
+    def needs_resize(self):
+        return self.get_load_factor() >= self._load_factor
+
+    def hash_function(self, world_coord):
+        """H(x,y,z) = (x*p1 xor y*p2 xor z*p3) mod n (reference hash_fusion.py:182-190)."""
+        x, y, z = (int(v) for v in world_coord[:3])
+        return ((x * P1) ^ (y * P2) ^ (z * P3)) % self._table_size
+
+    def sync(self):
+        _capi.check(self._lib.vh_sync(self._handle))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _capi.check(self._lib.vh_last_kernel_ms(self._handle, C.byref(ms)))
+        return ms.value
+
+    def get_mesh(self):
+        """Marching-cubes mesh of the scattered volume (reference hash_fusion.py:465-485)."""
+        from . import meshing
+        t, c = self.get_volume()
+        return meshing.mesh(t, c, self._voxel_size, self._vol_origin, self._color_const)
+
+    def get_point_cloud(self):
+        """Surface points with colours (reference hash_fusion.py:487-507)."""
+        from . import meshing
+        t, c = self.get_volume()
+        return meshing.point_cloud(t, c, self._voxel_size, self._vol_origin, self._color_const)
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle:
+            self._lib.vh_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
