@@ -113,6 +113,8 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     f->neg_trunc = -g.trunc;
     f->obs = obs;
     f->obs_f = (float)obs;
+    f->fast_w = ((double)(float)obs == obs && obs >= 0.0009765625 && obs <= 1024.0) ? 1 : 0;
+    f->unit_w = 0; // set by the handle, which knows the history of obs_weight
     f->H = H;
     f->W = W;
     f->depth = nullptr;
@@ -295,6 +297,7 @@ struct tsdf_grid {
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
+    bool unit_w = true; // every frame so far had obs_weight == 1 (weights are integers)
 };
 
 static int grid_free(tsdf_grid *g)
@@ -378,6 +381,8 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     cudaStream_t s = g->io.compute;
     f.depth = d_depth;
     f.cfold = g->io.d_cfold;
+    g->unit_w = g->unit_w && f.obs == 1.0;
+    f.unit_w = g->unit_w ? 1 : 0;
     if ((rc = g->io.begin_kernels())) return rc;
     CUDA_TRY(cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), s));
     launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->fs, H * W, g->sm_count, s);

@@ -1,7 +1,8 @@
 // dense_kernels.cu -- sm_100a kernels of the dense brick grid (K1 of SURVEY.md section 2a).
 //
 // Data layout in HBM: the grid is stored as 8x8x8-voxel bricks, one 6 KB record per brick:
-//   record = [512 tsdf | 512 weight | 512 colour] float32, voxel order (x*8 + y)*8 + z.
+//   record = [512 tsdf f32 | 512 weight f32 | 512 colour u32 (B<<16|G<<8|R, the integer value of
+//   the reference's float encoding)], voxel order (x*8 + y)*8 + z.
 // A z-run of 8 voxels is one 32 B sector per plane; a warp's float4 accesses cover 512 B
 // contiguous, so every DRAM transaction is a full sector and bricks the frame cannot touch are
 // never read.  Brick (bx,by,bz) of this rank lives at index ((bx/world)*nby + by)*nbz + bz.
@@ -65,10 +66,103 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
     }
 }
 
+// Per-thread body shared by the dense and the hash integrate kernels: geometry of the thread's
+// four z-consecutive voxels, then read-modify-write of its float4 per plane.
+//   lattice: wx, wy of the thread's column, wz[4] of its voxels; zvalid: bit e set if voxel e exists.
+//   rec: the thread's float4 slot inside the brick record.  Returns the number of voxels updated.
+// Straight-line fast paths for 4 voxels (ILP), rare cases (IEEE-division pixel, band / general
+// weights) peeled into per-bit loops.  The voxel record is requested as soon as one voxel
+// projects into the image, together with the depth pixels, so the three dependent latencies
+// (depth, record, colour) overlap; the record bypasses L1 (streamed once per frame) so L1 keeps
+// the depth / colour pixels.
+template <bool UNIT_W>
+__device__ __forceinline__ unsigned integrate_column4(const FrameParams &f, double wx, double wy, const double wz[4],
+                                                      unsigned zvalid, float *rec)
+{
+    const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
+    const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
+    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
+    double Z[4], ax[4], ay[4];
+    int pix[4];
+    unsigned cand = 0, exact = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        unsigned fl;
+        int pu, pv;
+        Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pu, pv, fl);
+        pix[e] = pv * f.W + pu;
+        cand |= (fl & 1u) << e;
+        exact |= ((fl >> 1) & 1u) << e;
+    }
+    exact &= zvalid;
+    cand &= zvalid;
+    if (exact) { // ~2^-15 of the voxels
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if ((exact >> e) & 1u) {
+                const int p = exact_pixel(ax[e], ay[e], Z[e], f.cx, f.cy, f.W, f.H);
+                if (p >= 0) { pix[e] = p; cand |= 1u << e; }
+            }
+    }
+    if (!cand) return 0;
+    // depth test (grid_fusion.py:278-286); record and colour requests ride along
+    double d[4];
+    uint32_t nc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (!((cand >> e) & 1u)) pix[e] = 0;
+        d[e] = __ldg(f.depth + pix[e]);
+    }
+    const float4 T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
+    const float4 W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
+    const uint4 C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) nc[e] = __ldg(f.cfold + pix[e]);
+    double diff[4];
+    unsigned pass = 0, band = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        diff[e] = __dadd_rn(d[e], -Z[e]);
+        if (d[e] > 0.0 && diff[e] >= f.neg_trunc) pass |= 1u << e;
+        if (diff[e] < f.trunc) band |= 1u << e;
+    }
+    pass &= cand;
+    if (!pass) return 0;
+    band &= pass;
+    float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
+    uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
+    unsigned slow = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float we = w[e];
+        uint32_t ce = c[e];
+        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, (band >> e) & 1u, nc[e]);
+        const bool on = (pass >> e) & 1u;
+        if (on && ok) { w[e] = we; c[e] = ce; }
+        if (on && !ok) slow |= 1u << e;
+    }
+    if (slow) { // truncation band, re-observed surface voxels, unusual obs_weight
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if ((slow >> e) & 1u) {
+                // grid_fusion.py:286: min(1, diff/trunc); the quotient is >= 1 exactly when diff >= trunc
+                const double dist = ((band >> e) & 1u) ? fmin(1.0, __ddiv_rn(diff[e], f.trunc)) : 1.0;
+                Voxel vin;
+                vin.tsdf = t[e]; vin.wgt = w[e]; vin.col = c[e];
+                const Voxel vo = update_voxel_slow(vin, dist, nc[e], f.obs, f.obs_f);
+                t[e] = vo.tsdf; w[e] = vo.wgt; c[e] = vo.col;
+            }
+        __stcs(reinterpret_cast<float4 *>(rec), make_float4(t[0], t[1], t[2], t[3]));
+    }
+    __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), make_float4(w[0], w[1], w[2], w[3]));
+    __stcs(reinterpret_cast<uint4 *>(rec + 2 * BRICK_VOX), make_uint4(c[0], c[1], c[2], c[3]));
+    return __popc(pass);
+}
+
 // Persistent CTAs; one brick per iteration, thread t owns voxels (x = t>>4, y = (t>>1)&7,
-// z = 4*(t&1) .. +3): one float4 per plane.  Geometry first (float64, no voxel traffic), then
-// only threads with at least one passing voxel read-modify-write their 3 x 16 B.
-__global__ void __launch_bounds__(INTEGRATE_THREADS, 6)
+// z = 4*(t&1) .. +3): one float4 per plane.
+template <bool UNIT_W>
+__global__ void __launch_bounds__(INTEGRATE_THREADS, 4)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
                   FrameScratch *fs, Totals *tot)
 {
@@ -81,31 +175,13 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly, gz0 = br.z * BRICK + lz0;
         if (gx >= v.dim_x || gy >= v.dim_y || gz0 >= v.dim_z) continue;
         const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
-        const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
-        const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
-        const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
         const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0));
         const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0) + 1);
         const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
-        double dist[4];
-        int pix[4];
-        unsigned mask = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (gz0 + e < v.dim_z && project_voxel(f, cX, cY, cZ, wz[e], dist[e], pix[e])) mask |= 1u << e;
-        if (!mask) continue;
-        float *rec = bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 4 * t;
-        float4 T4 = *reinterpret_cast<float4 *>(rec);
-        float4 W4 = *reinterpret_cast<float4 *>(rec + BRICK_VOX);
-        float4 C4 = *reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX);
-        if (mask & 1u) update_voxel(f, T4.x, W4.x, C4.x, dist[0], pix[0]);
-        if (mask & 2u) update_voxel(f, T4.y, W4.y, C4.y, dist[1], pix[1]);
-        if (mask & 4u) update_voxel(f, T4.z, W4.z, C4.z, dist[2], pix[2]);
-        if (mask & 8u) update_voxel(f, T4.w, W4.w, C4.w, dist[3], pix[3]);
-        *reinterpret_cast<float4 *>(rec) = T4;
-        *reinterpret_cast<float4 *>(rec + BRICK_VOX) = W4;
-        *reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX) = C4;
-        my_updates += __popc(mask);
+        const int left = v.dim_z - gz0;
+        const unsigned zvalid = left >= 4 ? 15u : ((1u << left) - 1u);
+        my_updates += integrate_column4<UNIT_W>(f, wx, wy, wz, zvalid,
+                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 4 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0 && my_updates) {
@@ -129,7 +205,7 @@ __global__ void k_unbrick(const float *__restrict__ bricks, int n_x, int dim_y, 
         const float *rec = bricks + brick * BRICK_FLOATS + ((i & 7) * 64 + (j & 7) * 8 + (k & 7));
         if (tsdf) tsdf[o] = __ldg(rec);
         if (wgt) wgt[o] = __ldg(rec + BRICK_VOX);
-        if (col) col[o] = __ldg(rec + 2 * BRICK_VOX);
+        if (col) col[o] = (float)__float_as_uint(__ldg(rec + 2 * BRICK_VOX)); // packed B<<16|G<<8|R -> f32 encoding
     }
 }
 
@@ -161,14 +237,17 @@ void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int
 int integrate_dense_ctas_per_sm()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense, INTEGRATE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense<true>, INTEGRATE_THREADS, 0);
     return n > 0 ? n : 1;
 }
 
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
                             FrameScratch *fs, Totals *tot, int grid, cudaStream_t s)
 {
-    k_integrate_dense<<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
+    if (f.unit_w)
+        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
+    else
+        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
 }
 
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
