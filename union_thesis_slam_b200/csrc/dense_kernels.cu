@@ -66,87 +66,73 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
     }
 }
 
-// Per-thread body shared by the dense and the hash integrate kernels: geometry of the thread's
-// four z-consecutive voxels, then read-modify-write of its float4 per plane.
-//   lattice: wx, wy of the thread's column, wz[4] of its voxels; zvalid: bit e set if voxel e exists.
-//   rec: the thread's float4 slot inside the brick record.  Returns the number of voxels updated.
+// Per-thread body shared by the dense and the hash integrate kernels: geometry of four
+// z-consecutive voxels of one (x, y) column, then read-modify-write of their float4 per plane.
+//   cX/cY/cZ: the column's partial sums fma(T[r][1], wy, T[r][0]*wx); wz[4]: lattice z of the
+//   voxels; nvalid: how many of the four exist (z < dim_z).  rec: the float4 slot inside the brick
+//   record.  Returns the number of voxels updated.
 // Straight-line fast paths for 4 voxels (ILP), rare cases (IEEE-division pixel, band / general
-// weights) peeled into per-bit loops.  The voxel record is requested as soon as one voxel
-// projects into the image, together with the depth pixels, so the three dependent latencies
-// (depth, record, colour) overlap; the record bypasses L1 (streamed once per frame) so L1 keeps
-// the depth / colour pixels.
+// weights) peeled off.  The voxel record is requested as soon as one voxel projects into the
+// image, together with the depth pixels, so the three dependent latencies (depth, record,
+// colour) overlap; the record bypasses L1 (streamed once per frame) so L1 keeps the depth /
+// colour pixels.
 template <bool UNIT_W>
-__device__ __forceinline__ unsigned integrate_column4(const FrameParams &f, double wx, double wy, const double wz[4],
-                                                      unsigned zvalid, float *rec)
+__device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double cX, double cY, double cZ,
+                                                   const double wz[4], int nvalid, float *rec)
 {
-    const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
-    const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
-    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
     double Z[4], ax[4], ay[4];
     int pix[4];
-    unsigned cand = 0, exact = 0;
+    bool cand[4], exact[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        unsigned fl;
-        int pu, pv;
-        Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pu, pv, fl);
-        pix[e] = pv * f.W + pu;
-        cand |= (fl & 1u) << e;
-        exact |= ((fl >> 1) & 1u) << e;
+        Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pix[e], cand[e], exact[e]);
+        if (e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
     }
-    exact &= zvalid;
-    cand &= zvalid;
-    if (exact) { // ~2^-15 of the voxels
+    if (exact[0] || exact[1] || exact[2] || exact[3]) { // ~2^-15 of the voxels
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if ((exact >> e) & 1u) {
+            if (exact[e]) {
                 const int p = exact_pixel(ax[e], ay[e], Z[e], f.cx, f.cy, f.W, f.H);
-                if (p >= 0) { pix[e] = p; cand |= 1u << e; }
+                if (p >= 0) { pix[e] = p; cand[e] = true; }
             }
     }
-    if (!cand) return 0;
+    if (!(cand[0] || cand[1] || cand[2] || cand[3])) return 0;
     // depth test (grid_fusion.py:278-286); record and colour requests ride along
     double d[4];
     uint32_t nc[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        if (!((cand >> e) & 1u)) pix[e] = 0;
-        d[e] = __ldg(f.depth + pix[e]);
-    }
+    for (int e = 0; e < 4; ++e) d[e] = __ldg(f.depth + pix[e]);
     const float4 T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
     const float4 W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
     const uint4 C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
 #pragma unroll
     for (int e = 0; e < 4; ++e) nc[e] = __ldg(f.cfold + pix[e]);
     double diff[4];
-    unsigned pass = 0, band = 0;
+    bool pass[4], band[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         diff[e] = __dadd_rn(d[e], -Z[e]);
-        if (d[e] > 0.0 && diff[e] >= f.neg_trunc) pass |= 1u << e;
-        if (diff[e] < f.trunc) band |= 1u << e;
+        pass[e] = cand[e] && d[e] > 0.0 && diff[e] >= f.neg_trunc;
+        band[e] = diff[e] < f.trunc;
     }
-    pass &= cand;
-    if (!pass) return 0;
-    band &= pass;
+    if (!(pass[0] || pass[1] || pass[2] || pass[3])) return 0;
     float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
     uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
-    unsigned slow = 0;
+    bool slow[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         float we = w[e];
         uint32_t ce = c[e];
-        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, (band >> e) & 1u, nc[e]);
-        const bool on = (pass >> e) & 1u;
-        if (on && ok) { w[e] = we; c[e] = ce; }
-        if (on && !ok) slow |= 1u << e;
+        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, band[e], nc[e]);
+        if (pass[e] && ok) { w[e] = we; c[e] = ce; }
+        slow[e] = pass[e] && !ok;
     }
-    if (slow) { // truncation band, re-observed surface voxels, unusual obs_weight
+    if (slow[0] || slow[1] || slow[2] || slow[3]) { // truncation band, re-observed surface voxels, unusual obs_weight
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if ((slow >> e) & 1u) {
+            if (slow[e]) {
                 // grid_fusion.py:286: min(1, diff/trunc); the quotient is >= 1 exactly when diff >= trunc
-                const double dist = ((band >> e) & 1u) ? fmin(1.0, __ddiv_rn(diff[e], f.trunc)) : 1.0;
+                const double dist = band[e] ? fmin(1.0, __ddiv_rn(diff[e], f.trunc)) : 1.0;
                 Voxel vin;
                 vin.tsdf = t[e]; vin.wgt = w[e]; vin.col = c[e];
                 const Voxel vo = update_voxel_slow(vin, dist, nc[e], f.obs, f.obs_f);
@@ -156,32 +142,54 @@ __device__ __forceinline__ unsigned integrate_column4(const FrameParams &f, doub
     }
     __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), make_float4(w[0], w[1], w[2], w[3]));
     __stcs(reinterpret_cast<uint4 *>(rec + 2 * BRICK_VOX), make_uint4(c[0], c[1], c[2], c[3]));
-    return __popc(pass);
+    return (unsigned)pass[0] + (unsigned)pass[1] + (unsigned)pass[2] + (unsigned)pass[3];
 }
 
-// Persistent CTAs; one brick per iteration, thread t owns voxels (x = t>>4, y = (t>>1)&7,
-// z = 4*(t&1) .. +3): one float4 per plane.
+// One (x, y) column of a brick: 8 voxels as two quads.  Returns the number of voxels updated.
 template <bool UNIT_W>
-__global__ void __launch_bounds__(INTEGRATE_THREADS, 4)
+__device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, const VolumeParams &v, int gx, int gy,
+                                                      int gz0, float *rec)
+{
+    const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
+    const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
+    const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
+    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
+    unsigned n = 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int gz = gz0 + 4 * h;
+        const int nvalid = v.dim_z - gz;
+        if (nvalid <= 0) break;
+        const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz));
+        const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz) + 1);
+        const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
+        n += integrate_quad<UNIT_W>(f, cX, cY, cZ, wz, nvalid, rec + 4 * h);
+    }
+    return n;
+}
+
+// Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
+// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.  The next list entry is
+// fetched while the current brick is processed.
+template <bool UNIT_W>
+__global__ void __launch_bounds__(INTEGRATE_THREADS, 10)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
                   FrameScratch *fs, Totals *tot)
 {
     const int n = fs->vis_count;
     const int t = threadIdx.x;
-    const int lx = t >> 4, ly = (t >> 1) & 7, lz0 = (t & 1) * 4;
+    const int lx = t >> 3, ly = t & 7;
     unsigned my_updates = 0;
-    for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int4 br = __ldg(reinterpret_cast<const int4 *>(list) + b);
-        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly, gz0 = br.z * BRICK + lz0;
-        if (gx >= v.dim_x || gy >= v.dim_y || gz0 >= v.dim_z) continue;
-        const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
-        const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0));
-        const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz0) + 1);
-        const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
-        const int left = v.dim_z - gz0;
-        const unsigned zvalid = left >= 4 ? 15u : ((1u << left) - 1u);
-        my_updates += integrate_column4<UNIT_W>(f, wx, wy, wz, zvalid,
-                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 4 * t);
+    int b = blockIdx.x;
+    int4 br_next = make_int4(0, 0, 0, 0);
+    if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
+    for (; b < n; b += gridDim.x) {
+        const int4 br = br_next;
+        if (b + (int)gridDim.x < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
+        if (gx >= v.dim_x || gy >= v.dim_y) continue;
+        my_updates += integrate_column8<UNIT_W>(f, v, gx, gy, br.z * BRICK,
+                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0 && my_updates) {
