@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- TSDF integration throughput on B200 (BASELINE.json metric: voxel-updates/s and
+frames/s, dense grid and voxel-block hash map, against the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one RGB-D frame integrated into the map.  Workload = BASELINE.json configs[3]: a
+synthetic 10 m x 10 m x 4 m room at 1 cm voxels (1000 x 1000 x 400 = 4.0e8 voxels, 4.8 GB of
+voxel state, far larger than the 126 MB L2, so every frame streams its bricks from HBM), 640x480
+frames on a seeded trajectory (union_thesis_slam_b200/synth.py), obs_weight 1.  With N > 1 the
+same room is split into brick-thick cyclic x-sheets (rank = sheet % N): strong scaling, no
+per-frame collective.  The hash-map line (configs[4]-shaped stream into the same room, 2 cm
+voxels) rides in the "hash" object of the same JSON line.
+
+Printed keys follow the driver contract; see DESIGN.md section "Measurement" for definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROOM = (10.0, 10.0, 4.0)
+VOXEL = 0.01
+IM_W, IM_H = 640, 480
+N_FRAMES = 32           # distinct frames kept resident in HBM and replayed in order
+HASH_VOXEL = 0.02
+CPU_SHEET_STRIDE = 16   # cpu baseline integrates every 16th x-sheet of the same grid
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "20"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def make_frames(n, width=IM_W, height=IM_H):
+    from union_thesis_slam_b200 import synth
+    room = synth.room_bounds(ROOM)
+    frames, K = synth.room_stream(n, room, width=width, height=height, seed=0)
+    return room, frames, K
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_port(frames, K, room, voxel, steps, warmup, stride=CPU_SHEET_STRIDE):
+    """Times the CPU oracle (C/OpenMP restatement of the reference's numba path) on all host
+    threads over a bounded sample: every `stride`-th x-sheet of the same grid."""
+    from oracle import oracle
+    dim, _ = oracle.volume_geometry(room.copy(), voxel)
+    xs = np.arange(0, int(dim[0]), stride, dtype=np.int64)
+    vol = oracle.OracleTSDFVolume(room.copy(), voxel, xs=xs, nthreads=0)
+    cores = int(oracle.lib().oracle_max_threads())
+    for i in range(warmup):
+        c, d, p = frames[i % len(frames)]
+        vol.integrate(c, d, K, p)
+    t0 = time.perf_counter()
+    upd = 0
+    for i in range(steps):
+        c, d, p = frames[(warmup + i) % len(frames)]
+        upd += vol.integrate(c, d, K, p)
+    dt = time.perf_counter() - t0
+    sample = "every %dth x-sheet (%d of %d sheets, %.2e voxels) of the %.3g m room grid, %d frames" % (
+        stride, len(xs), int(dim[0]), len(xs) * float(dim[1]) * float(dim[2]), voxel, steps)
+    return dict(value=upd / dt, unit="voxel-updates/s", cores=cores, kind="port", sample=sample,
+                frames_per_s_sample=steps / dt, seconds=dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path timed on this box's host cores.  The reference
+    is pure Python + numba and does not travel to the GPU box; its arithmetic is restated in
+    oracle/tsdf_oracle.c (bit-identical, tests/test_oracle_golden.py), which is what runs here."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    room, frames, K = make_frames(min(N_FRAMES, args.warmup + args.steps))
+    r = cpu_port(frames, K, room, VOXEL, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "tsdf_voxel_updates_per_s", "value": r["value"], "unit": "voxel-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": r["frames_per_s_sample"], "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(world):
+    return {"workload": "BASELINE.json configs[3]: synthetic 10x10x4 m room, dense grid, 1 cm voxels "
+                        "(1000x1000x400 = 4.0e8 voxels, 4.8 GB), 640x480 frames, seeded trajectory",
+            "voxel_size_m": VOXEL, "grid": [1000, 1000, 400], "image": [IM_W, IM_H],
+            "frames_resident": N_FRAMES, "obs_weight": 1.0,
+            "partition": "cyclic brick-thick x-sheets, rank = sheet %% %d" % world,
+            "l2_policy": "working set (4.8 GB voxel state, 2-4 GB touched per frame) exceeds the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from union_thesis_slam_b200 import grid_fusion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    room, frames, K = make_frames(N_FRAMES)
+    npix = IM_W * IM_H
+    d_frames = [(torch.from_numpy(c).to(dev), torch.from_numpy(d).to(dev), np.linalg.inv(p)) for c, d, p in frames]
+    vol = grid_fusion.TSDFVolume(room.copy(), VOXEL, rank=rank, world_size=world, device=local)
+    stream = torch.cuda.ExternalStream(vol.cuda_stream(), device=dev)
+
+    def step(i):
+        dc, dd, tinv = d_frames[i % N_FRAMES]
+        vol.integrate_device(dc, dd, IM_H, IM_W, K, tinv, 1.0)
+
+    launches_per_step = 3  # prep_frame, cull_bricks, integrate_dense (+ one 32-byte memset)
+    for i in range(args.warmup):
+        step(i)
+    vol.sync()
+
+    # ---- timed region: frames resident in HBM, device-timed on the launching stream ----------
+    sampler = ClockSampler(local) if rank == 0 else None
+    u0 = vol.stats()["updated_total"]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    vol.sync()
+    barrier()
+    ms = allreduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if sampler else None
+    upd = allreduce(float(vol.stats()["updated_total"] - u0), dist.ReduceOp.SUM if world > 1 else None)
+    value = upd / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (integrate_dense), measured live per launch ----------
+    vol.set_profiling(True)
+    k_ms, k_bytes, k_upd = 0.0, 0.0, 0
+    for i in range(args.steps):
+        step(args.warmup + i)
+        st = vol.last_stage_ms()
+        u = vol.stats()["updated_last"]
+        k_ms += st[-1]
+        k_upd += u
+        k_bytes += 24.0 * u + 12.0 * npix
+    vol.set_profiling(False)
+    peak, peak_src = peaks()
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_integrate_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": k_bytes / args.steps,
+                "bytes_model": "24 B x voxels updated + 12 B x pixels (SURVEY 8d)",
+                "kernel_ms_per_launch": k_ms / args.steps, "traffic": None,
+                # same bytes over the whole timed step (prepare + cull + integrate), single GPU only
+                "frac_whole_step": (k_bytes / (ms * 1e-3) / 1e9) / peak if world == 1 else None}
+    traffic_file = os.path.join(ROOT, "profiles", "dense_traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+
+    # ---- end to end through the drop-in API: pinned host frames in, counters out, every step --
+    h_frames = []
+    for c, d, p in frames:
+        pc, pd = torch.from_numpy(c).pin_memory(), torch.from_numpy(d).pin_memory()
+        h_frames.append((pc.numpy(), pd.numpy(), p, pc, pd))
+    for i in range(min(3, args.warmup)):
+        c, d, p = h_frames[i % N_FRAMES][:3]
+        vol.integrate(c, d, K, p, obs_weight=1.)
+    vol.sync()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_upd = 0
+    for i in range(args.steps):
+        c, d, p = h_frames[(args.warmup + i) % N_FRAMES][:3]
+        vol.integrate(c, d, K, p, obs_weight=1.)
+        e2e_upd += vol.stats()["updated_last"]  # device -> host read of the step's result
+    vol.sync()
+    barrier()
+    e2e_s = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_upd = allreduce(float(e2e_upd), dist.ReduceOp.SUM if world > 1 else None)
+    e2e = {"value": e2e_upd / e2e_s, "unit": "voxel-updates/s", "h2d_bytes_per_step": npix * (8 + 3),
+           "d2h_bytes_per_step": 64, "frames_per_s": args.steps / e2e_s,
+           "api": "TSDFVolume.integrate(color, depth, K, pose) + stats() per frame, pinned host buffers"}
+
+    line = {
+        "metric": "tsdf_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world), "frames_per_s": args.steps / (ms * 1e-3),
+        "voxel_updates_per_step": upd / args.steps, "roofline": roofline, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_hash:
+        try:
+            line["hash"] = bench_hash(args, dev, local, frames, K, room, peak)
+        except Exception as exc:  # the hash line must never hide the dense result
+            line["hash"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_port(frames, K, room, VOXEL, steps=4, warmup=1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_hash(args, dev, local, frames, K, room, peak):
+    """Voxel-block hash map on the same stream (2 cm voxels, 8^3 blocks), single GPU."""
+    import torch
+    from union_thesis_slam_b200 import hash_fusion
+    nblocks = int(np.prod(np.ceil(np.array(ROOM) / HASH_VOXEL / 8)))
+    ht = hash_fusion.HashTable(room.copy(), HASH_VOXEL, map_size=4 * nblocks, heap_blocks=nblocks, device=local)
+    d_frames = [(torch.from_numpy(c).to(dev), torch.from_numpy(d).to(dev), np.linalg.inv(p)) for c, d, p in frames]
+    steps = args.steps
+    for i in range(args.warmup):
+        dc, dd, ti = d_frames[i % N_FRAMES]
+        ht.integrate_device(dc, dd, IM_H, IM_W, K, ti, 1.0)
+    ht.sync()
+    s0 = ht.stats()
+    tot_ms, tot_bytes = 0.0, 0.0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        dc, dd, ti = d_frames[(args.warmup + i) % N_FRAMES]
+        ht.integrate_device(dc, dd, IM_H, IM_W, K, ti, 1.0)
+        tot_ms += ht.last_kernel_ms()
+        st = ht.stats()
+        tot_bytes += 24.0 * st["updated_last"] + 16.0 * st["candidates_last"] + 12.0 * IM_W * IM_H
+    wall = time.perf_counter() - t0
+    s1 = ht.stats()
+    upd = s1["updated_total"] - s0["updated_total"]
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    return {"metric": "tsdf_voxel_updates_per_s", "value": upd / (tot_ms * 1e-3), "unit": "voxel-updates/s",
+            "frames_per_s": steps / (tot_ms * 1e-3), "ms_per_step": tot_ms / steps,
+            "voxel_size_m": HASH_VOXEL, "blocks": s1["blocks"], "table_slots": s1["table_slots"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "bytes_model": "24 B x voxels updated + 16 B x candidate keys + 12 B x pixels, whole "
+                                        "pipeline (ray walk + insert + compaction + integrate) device time"},
+            "wall_s": wall}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1024)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-hash", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -85,6 +85,13 @@ int tsdf_grid_sync(tsdf_grid *g);
 /* Milliseconds the device spent on the last integrate call's kernels (CUDA events on the
  * handle's stream; waits for them). */
 int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms);
+/* Measurement aids.  set_profiling(1) records an extra event between the frame-preparation
+ * kernels (colour fold, brick culling) and the integrate kernel; last_stage_ms then returns
+ * n = 2 durations {prepare+cull, integrate} of the last frame (n = 1: the whole frame).
+ * stream() exposes the handle's cudaStream_t so callers can record their own events on it. */
+int tsdf_grid_set_profiling(tsdf_grid *g, int on);
+int tsdf_grid_last_stage_ms(tsdf_grid *g, float ms[4], int *n);
+int tsdf_grid_stream(tsdf_grid *g, void **stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Voxel-block hash map.  Replaces hash_fusion.HashTable (hash_fusion.py:29-507) on the

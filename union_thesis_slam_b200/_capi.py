@@ -32,6 +32,9 @@ SYMBOLS = [
     ("tsdf_grid_stats", _i, [_p, _p]),
     ("tsdf_grid_sync", _i, [_p]),
     ("tsdf_grid_last_kernel_ms", _i, [_p, _p]),
+    ("tsdf_grid_set_profiling", _i, [_p, _i]),
+    ("tsdf_grid_last_stage_ms", _i, [_p, _p, _p]),
+    ("tsdf_grid_stream", _i, [_p, _pp]),
     ("vh_create", _i, [_p, _p, _d, _d, _i64, _i64, _i, _i, _i, _pp]),
     ("vh_destroy", _i, [_p]),
     ("vh_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),

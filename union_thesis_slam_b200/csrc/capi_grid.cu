@@ -141,6 +141,7 @@ int FrameIO::init()
     }
     CUDA_TRY(cudaEventCreate(&k_begin));
     CUDA_TRY(cudaEventCreate(&k_end));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&k_mark[i]));
     return TSDF_OK;
 }
 
@@ -221,6 +222,28 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
 int FrameIO::begin_kernels()
 {
     CUDA_TRY(cudaEventRecord(k_begin, compute));
+    n_marks = 0;
+    return TSDF_OK;
+}
+
+int FrameIO::mark()
+{
+    if (n_marks < 3) CUDA_TRY(cudaEventRecord(k_mark[n_marks++], compute));
+    return TSDF_OK;
+}
+
+int FrameIO::last_stage_ms(float ms[4], int *n)
+{
+    BAD_ARG(!ms || !n, "NULL argument");
+    BAD_ARG(!timed, "no frame integrated yet");
+    CUDA_TRY(cudaEventSynchronize(k_end));
+    cudaEvent_t ev[5];
+    int k = 0;
+    ev[k++] = k_begin;
+    for (int i = 0; i < n_marks; ++i) ev[k++] = k_mark[i];
+    ev[k++] = k_end;
+    for (int i = 0; i + 1 < k; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    *n = k - 1;
     return TSDF_OK;
 }
 
@@ -257,6 +280,8 @@ void FrameIO::release()
         if (slot_free[i]) cudaEventDestroy(slot_free[i]);
     }
     if (d_cfold) cudaFree(d_cfold);
+    for (int i = 0; i < 3; ++i)
+        if (k_mark[i]) cudaEventDestroy(k_mark[i]);
     if (k_begin) cudaEventDestroy(k_begin);
     if (k_end) cudaEventDestroy(k_end);
     if (compute) cudaStreamDestroy(compute);
@@ -297,6 +322,7 @@ struct tsdf_grid {
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
+    bool profile_stages = false;
     bool unit_w = true; // every frame so far had obs_weight == 1 (weights are integers)
 };
 
@@ -387,6 +413,7 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     CUDA_TRY(cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), s));
     launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->fs, H * W, g->sm_count, s);
     launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->vis_list, g->fs, s);
+    if (g->profile_stages && (rc = g->io.mark())) return rc;
     launch_integrate_dense(f, g->geom.params(), g->vis_list, g->bricks, g->fs, g->tot, g->integrate_grid, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
@@ -503,4 +530,25 @@ extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
     return g->io.last_ms(ms);
+}
+
+extern "C" int tsdf_grid_set_profiling(tsdf_grid *g, int on)
+{
+    BAD_ARG(!g, "NULL handle");
+    g->profile_stages = on != 0;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_last_stage_ms(tsdf_grid *g, float ms[4], int *n)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    return g->io.last_stage_ms(ms, n);
+}
+
+extern "C" int tsdf_grid_stream(tsdf_grid *g, void **stream)
+{
+    BAD_ARG(!g || !stream, "NULL argument");
+    *stream = (void *)g->io.compute;
+    return TSDF_OK;
 }

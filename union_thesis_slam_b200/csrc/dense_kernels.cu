@@ -172,7 +172,7 @@ __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, cons
 // (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.  The next list entry is
 // fetched while the current brick is processed.
 template <bool UNIT_W>
-__global__ void __launch_bounds__(INTEGRATE_THREADS, 10)
+__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
                   FrameScratch *fs, Totals *tot)
 {
@@ -185,7 +185,11 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
     for (; b < n; b += gridDim.x) {
         const int4 br = br_next;
-        if (b + (int)gridDim.x < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+        if (b + (int)gridDim.x < n) {
+            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+            // pull the next brick's 6 KB record into L2 while this one is integrated
+            if (t == 0) prefetch_record_l2(bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS);
+        }
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
         my_updates += integrate_column8<UNIT_W>(f, v, gx, gy, br.z * BRICK,

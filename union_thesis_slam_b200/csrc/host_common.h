@@ -65,6 +65,8 @@ struct FrameIO {
     uint32_t *d_cfold = nullptr;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
     cudaEvent_t k_begin = nullptr, k_end = nullptr;
+    cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
+    int n_marks = 0;
     int next = 0, cur = -1;
     bool timed = false;
 
@@ -76,6 +78,8 @@ struct FrameIO {
     int ensure_cfold(int npix);
     int begin_kernels();
     int end_kernels(); // records timing + releases the upload slot
+    int mark(); // records a stage boundary (up to 3 per frame)
     int last_ms(float *ms);
+    int last_stage_ms(float ms[4], int *n); // durations of the stages delimited by mark()
     void release();
 };

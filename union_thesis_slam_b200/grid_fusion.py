@@ -153,6 +153,23 @@ class TSDFVolume:
         _capi.check(self._lib.tsdf_grid_last_kernel_ms(self._handle, C.byref(ms)))
         return ms.value
 
+    def set_profiling(self, on=True):
+        _capi.check(self._lib.tsdf_grid_set_profiling(self._handle, int(bool(on))))
+
+    def last_stage_ms(self):
+        """Device milliseconds of the last frame's stages: [prepare+cull, integrate] with
+        profiling on, [whole frame] otherwise."""
+        ms = (C.c_float * 4)()
+        n = C.c_int()
+        _capi.check(self._lib.tsdf_grid_last_stage_ms(self._handle, ms, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
+    def cuda_stream(self):
+        """Raw cudaStream_t (int) the kernels run on; wrap with torch.cuda.ExternalStream."""
+        s = C.c_void_p()
+        _capi.check(self._lib.tsdf_grid_stream(self._handle, C.byref(s)))
+        return s.value or 0
+
     def get_point_cloud(self):
         """Surface points with colours (reference grid_fusion.py:322-341)."""
         from . import meshing
