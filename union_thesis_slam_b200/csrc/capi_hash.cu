@@ -1,22 +1,371 @@
 // capi_hash.cu -- C ABI of the voxel-block hash map (include/tsdf_b200.h, vh_*).
-// PLACEHOLDER while the dense path is brought up on the GPU: every entry point fails loudly.
+#include <algorithm>
+#include <new>
+#include <vector>
+
 #include "host_common.h"
 
-#define NOT_YET                                              \
-    tsdf_set_error("%s: hash map not implemented yet", __func__); \
-    return TSDF_ERR_BAD_ARG
+struct tsdf_hash {
+    int device = 0, sm_count = 0, rank = 0, world = 1;
+    VolumeGeom geom;
+    FrameIO io;
+    HashDev dev{};
+    int64_t table_slots = 0, heap_blocks = 0;
+    BrickRef *vis_list = nullptr;
+    FrameScratch *fs = nullptr;
+    Totals *tot = nullptr;
+    float *tile_dmax = nullptr;
+    int tile_cap = 0;
+    int *scratch_count = nullptr; // device int used by export / remove
+    int integrate_grid = 0;
+    int64_t frames = 0;
+    bool unit_w = true;
+    double walk_step_voxels = 4.0; // ray-walk sample spacing: half a block
+};
 
-extern "C" {
-int vh_create(const int64_t *, const float *, double, double, int64_t, int64_t, int, int, int, tsdf_hash **) { NOT_YET; }
-int vh_destroy(tsdf_hash *) { return TSDF_OK; }
-int vh_integrate(tsdf_hash *, const uint8_t *, const double *, int, int, const double *, const double *, double) { NOT_YET; }
-int vh_integrate_device(tsdf_hash *, const uint8_t *, const double *, int, int, const double *, const double *, double) { NOT_YET; }
-int vh_stats(tsdf_hash *, int64_t *) { NOT_YET; }
-int vh_num_blocks(tsdf_hash *, int64_t *) { NOT_YET; }
-int vh_export_blocks(tsdf_hash *, int64_t, int64_t *, int32_t *, float *) { NOT_YET; }
-int vh_to_dense(tsdf_hash *, float *, float *, float *) { NOT_YET; }
-int vh_to_dense_device(tsdf_hash *, float *, float *, float *) { NOT_YET; }
-int vh_remove_blocks(tsdf_hash *, const int32_t *, int64_t, int64_t *) { NOT_YET; }
-int vh_sync(tsdf_hash *) { NOT_YET; }
-int vh_last_kernel_ms(tsdf_hash *, float *) { NOT_YET; }
+static int hash_free(tsdf_hash *h)
+{
+    if (!h) return TSDF_OK;
+    cudaSetDevice(h->device);
+    h->io.release();
+    h->geom.release();
+    void *ptrs[] = {h->dev.keys, h->dev.vals, h->dev.entries, h->dev.n_entries, h->dev.heap, h->dev.heap_top,
+                    h->dev.blocks, h->vis_list, h->fs, h->tot, h->tile_dmax, h->scratch_count};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete h;
+    return TSDF_OK;
+}
+
+extern "C" int vh_create(const int64_t dim[3], const float origin[3], double voxel_size, double trunc,
+                         int64_t table_slots, int64_t heap_blocks, int device, int rank, int world, tsdf_hash **out)
+{
+    BAD_ARG(!out, "out is NULL");
+    *out = nullptr;
+    BAD_ARG(world < 1 || rank < 0 || rank >= world, "bad rank/world %d/%d", rank, world);
+    BAD_ARG(table_slots <= 0 || table_slots > ((int64_t)1 << 30), "table_slots %lld out of range", (long long)table_slots);
+    BAD_ARG(heap_blocks <= 0 || heap_blocks > ((int64_t)1 << 30), "heap_blocks %lld out of range", (long long)heap_blocks);
+    int sm = 0;
+    int rc = tsdf_select_device(device, &sm);
+    if (rc) return rc;
+    tsdf_hash *h = new (std::nothrow) tsdf_hash;
+    BAD_ARG(!h, "out of host memory");
+    h->device = device;
+    h->sm_count = sm;
+    h->rank = rank;
+    h->world = world;
+    if ((rc = h->geom.init(dim, origin, voxel_size, trunc)) || (rc = h->io.init())) {
+        hash_free(h);
+        return rc;
+    }
+    for (int a = 0; a < 3; ++a)
+        if (h->geom.nb[a] >= (1 << 21)) {
+            hash_free(h);
+            tsdf_set_error("volume has too many blocks along axis %d for 21-bit key fields", a);
+            return TSDF_ERR_BAD_ARG;
+        }
+    int64_t S = 1024;
+    while (S < table_slots) S <<= 1;
+    h->table_slots = S;
+    h->heap_blocks = heap_blocks;
+    HashDev &d = h->dev;
+    d.mask = (uint32_t)(S - 1);
+    d.heap_cap = (int)heap_blocks;
+    d.rank = rank;
+    d.world = world;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d.keys, S * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&d.vals, S * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&d.entries, S * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&d.n_entries, sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&d.heap, heap_blocks * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&d.heap_top, sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list, S * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->fs, sizeof(FrameScratch))) != cudaSuccess ||
+        (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
+        (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
+        tsdf_set_error("device allocation failed (%lld slots, %lld blocks = %.2f GB): %s", (long long)S,
+                       (long long)heap_blocks, heap_blocks * 6144.0 / 1e9, cudaGetErrorString(e));
+        cudaGetLastError();
+        hash_free(h);
+        return TSDF_ERR_OOM;
+    }
+    cudaMemsetAsync(h->fs, 0, sizeof(FrameScratch), h->io.compute);
+    cudaMemsetAsync(h->tot, 0, sizeof(Totals), h->io.compute);
+    launch_hash_init(d, sm, h->io.compute);
+    h->integrate_grid = sm * integrate_hash_ctas_per_sm();
+    e = cudaStreamSynchronize(h->io.compute);
+    if (e != cudaSuccess) {
+        tsdf_set_error("hash map initialisation failed: %s", cudaGetErrorString(e));
+        hash_free(h);
+        return TSDF_ERR_CUDA;
+    }
+    *out = h;
+    return TSDF_OK;
+}
+
+extern "C" int vh_destroy(tsdf_hash *h) { return hash_free(h); }
+
+// 3x4 camera->world pose from the 4x4 inverse pose (general affine inverse, double precision).
+static int invert_affine(const double Ti[16], double P[12])
+{
+    const double a = Ti[0], b = Ti[1], c = Ti[2], d = Ti[4], e = Ti[5], f = Ti[6], g = Ti[8], hh = Ti[9], i = Ti[10];
+    const double det = a * (e * i - f * hh) - b * (d * i - f * g) + c * (d * hh - e * g);
+    if (!(fabs(det) > 1e-300) || !isfinite(det)) return -1;
+    const double r[9] = {(e * i - f * hh) / det, (c * hh - b * i) / det, (b * f - c * e) / det,
+                         (f * g - d * i) / det,  (a * i - c * g) / det,  (c * d - a * f) / det,
+                         (d * hh - e * g) / det, (b * g - a * hh) / det, (a * e - b * d) / det};
+    for (int row = 0; row < 3; ++row) {
+        for (int col = 0; col < 3; ++col) P[4 * row + col] = r[3 * row + col];
+        P[4 * row + 3] = -(r[3 * row] * Ti[3] + r[3 * row + 1] * Ti[7] + r[3 * row + 2] * Ti[11]);
+    }
+    return 0;
+}
+
+// Sticky error raised inside a kernel by an earlier frame (heap exhausted / table full).
+static int check_device_error(tsdf_hash *h)
+{
+    Totals tot;
+    CUDA_TRY(cudaMemcpy(&tot, h->tot, sizeof(tot), cudaMemcpyDeviceToHost));
+    if (tot.error) {
+        const int code = -(int)tot.error;
+        tsdf_set_error(code == TSDF_ERR_HEAP_EXHAUSTED
+                           ? "voxel-block heap exhausted (%lld blocks): blocks were dropped; create the map with more heap_blocks"
+                           : "hash table full (%lld slots): keys were dropped; create the map with more table_slots",
+                       (long long)(code == TSDF_ERR_HEAP_EXHAUSTED ? h->heap_blocks : h->table_slots));
+        return code;
+    }
+    return TSDF_OK;
+}
+
+static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
+                    CullParams &c, const double Tinv[16])
+{
+    int rc = h->io.ensure_cfold(H * W);
+    if (rc) return rc;
+    cudaStream_t s = h->io.compute;
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+    if (tiles_x * tiles_y > h->tile_cap) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (h->tile_dmax) cudaFree(h->tile_dmax);
+        h->tile_dmax = nullptr;
+        CUDA_TRY(cudaMalloc(&h->tile_dmax, (size_t)tiles_x * tiles_y * sizeof(float)));
+        h->tile_cap = tiles_x * tiles_y;
+    }
+    WalkParams w;
+    BAD_ARG(invert_affine(Tinv, w.P) != 0, "Tinv is singular");
+    w.ox = (double)h->geom.origin[0]; w.oy = (double)h->geom.origin[1]; w.oz = (double)h->geom.origin[2];
+    w.inv_vs = 1.0 / h->geom.vs;
+    w.step = h->walk_step_voxels * h->geom.vs;
+    w.trunc = h->geom.trunc;
+    w.fx = f.fx; w.fy = f.fy; w.cx = f.cx; w.cy = f.cy;
+    BAD_ARG(f.fx == 0.0 || f.fy == 0.0, "zero focal length");
+    // ||R||_2^2 = lambda_max(R^T R) <= 1 + ||R^T R - I||_F
+    double ef = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double dot = 0.0;
+            for (int k = 0; k < 3; ++k) dot += w.P[4 * k + i] * w.P[4 * k + j];
+            dot -= (i == j) ? 1.0 : 0.0;
+            ef += dot * dot;
+        }
+    w.pose_scale = sqrt(1.0 + sqrt(ef)) * 1.000001;
+    w.W = W; w.H = H; w.tiles_x = tiles_x; w.tiles_y = tiles_y;
+    w.dim_x = (int)h->geom.dim[0]; w.dim_y = (int)h->geom.dim[1]; w.dim_z = (int)h->geom.dim[2];
+
+    f.depth = d_depth;
+    f.cfold = h->io.d_cfold;
+    h->unit_w = h->unit_w && f.obs == 1.0;
+    f.unit_w = h->unit_w ? 1 : 0;
+    if ((rc = h->io.begin_kernels())) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->fs, 0, sizeof(FrameScratch), s));
+    launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->fs, H * W, h->sm_count, s);
+    launch_tile_maxdepth(d_depth, H, W, tiles_x, tiles_y, h->tile_dmax, s);
+    launch_walk_insert(w, h->dev, h->tile_dmax, h->fs, h->tot, s);
+    launch_compact_visible(f, c, h->dev, (int)h->table_slots, h->vis_list, h->fs, s);
+    launch_integrate_hash(f, h->geom.params(), h->dev, h->vis_list, h->fs, h->tot, h->integrate_grid, s);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = h->io.end_kernels())) return rc;
+    h->frames++;
+    return TSDF_OK;
+}
+
+extern "C" int vh_integrate(tsdf_hash *h, const uint8_t *rgb, const double *depth, int H, int W, const double K[9],
+                            const double Tinv[16], double obs_weight)
+{
+    BAD_ARG(!h || !rgb || !depth, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const uint8_t *d_rgb;
+    const double *d_depth;
+    if ((rc = h->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
+    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+}
+
+extern "C" int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,
+                                   const double K[9], const double Tinv[16], double obs_weight)
+{
+    BAD_ARG(!h || !d_rgb || !d_depth, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+}
+
+extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
+{
+    BAD_ARG(!h || !stats, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->io.compute));
+    FrameScratch fs;
+    Totals tot;
+    int n_entries = 0, heap_top = 0;
+    CUDA_TRY(cudaMemcpy(&fs, h->fs, sizeof(fs), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&tot, h->tot, sizeof(tot), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&n_entries, h->dev.n_entries, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&heap_top, h->dev.heap_top, sizeof(int), cudaMemcpyDeviceToHost));
+    stats[0] = h->heap_blocks - heap_top;
+    stats[1] = n_entries;
+    stats[2] = h->table_slots;
+    stats[3] = h->heap_blocks;
+    stats[4] = heap_top;
+    stats[5] = (int64_t)fs.updated;
+    stats[6] = (int64_t)tot.updated;
+    stats[7] = (int64_t)tot.last_visited;
+    stats[8] = (int64_t)tot.max_probe;
+    stats[9] = fs.new_keys;
+    stats[10] = h->frames;
+    stats[11] = fs.cand_count;
+    return check_device_error(h);
+}
+
+extern "C" int vh_num_blocks(tsdf_hash *h, int64_t *n)
+{
+    BAD_ARG(!h || !n, "NULL argument");
+    int64_t s[12];
+    const int rc = vh_stats(h, s);
+    *n = s[0];
+    return rc;
+}
+
+extern "C" int vh_sync(tsdf_hash *h)
+{
+    BAD_ARG(!h, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->io.copy));
+    CUDA_TRY(cudaStreamSynchronize(h->io.compute));
+    return check_device_error(h);
+}
+
+extern "C" int vh_last_kernel_ms(tsdf_hash *h, float *ms)
+{
+    BAD_ARG(!h, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return h->io.last_ms(ms);
+}
+
+extern "C" int vh_to_dense_device(tsdf_hash *h, float *d_tsdf, float *d_weight, float *d_color)
+{
+    BAD_ARG(!h, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    launch_scatter_dense(h->dev, (int)h->geom.dim[0], (int)h->geom.dim[1], (int)h->geom.dim[2], d_tsdf, d_weight,
+                         d_color, h->sm_count, h->io.compute);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->io.compute));
+    return check_device_error(h);
+}
+
+extern "C" int vh_to_dense(tsdf_hash *h, float *tsdf, float *weight, float *color)
+{
+    BAD_ARG(!h, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->geom.dim[0] * h->geom.dim[1] * h->geom.dim[2];
+    float *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, n * sizeof(float)));
+    float *host[3] = {tsdf, weight, color};
+    for (int p = 0; p < 3; ++p) {
+        if (!host[p]) continue;
+        launch_scatter_dense(h->dev, (int)h->geom.dim[0], (int)h->geom.dim[1], (int)h->geom.dim[2],
+                             p == 0 ? scratch : nullptr, p == 1 ? scratch : nullptr, p == 2 ? scratch : nullptr,
+                             h->sm_count, h->io.compute);
+        cudaError_t e = cudaMemcpyAsync(host[p], scratch, n * sizeof(float), cudaMemcpyDeviceToHost, h->io.compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->io.compute);
+        if (e != cudaSuccess) {
+            cudaFree(scratch);
+            tsdf_set_error("to_dense failed: %s", cudaGetErrorString(e));
+            return TSDF_ERR_CUDA;
+        }
+    }
+    cudaFree(scratch);
+    return check_device_error(h);
+}
+
+extern "C" int vh_export_blocks(tsdf_hash *h, int64_t capacity, int64_t *n, int32_t *keys, float *payload)
+{
+    BAD_ARG(!h || !n, "NULL argument");
+    BAD_ARG(capacity < 0, "negative capacity");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->io.compute;
+    const bool want = keys && payload && capacity > 0;
+    int32_t *d_keys = nullptr;
+    float *d_payload = nullptr;
+    if (want) {
+        CUDA_TRY(cudaMalloc(&d_keys, (size_t)capacity * 3 * sizeof(int32_t)));
+        cudaError_t e = cudaMalloc(&d_payload, (size_t)capacity * BRICK_FLOATS * sizeof(float));
+        if (e != cudaSuccess) {
+            cudaFree(d_keys);
+            cudaGetLastError();
+            tsdf_set_error("export scratch allocation failed: %s", cudaGetErrorString(e));
+            return TSDF_ERR_OOM;
+        }
+    }
+    cudaMemsetAsync(h->scratch_count, 0, sizeof(int), s);
+    launch_export_blocks(h->dev, want ? (int)capacity : 0, h->scratch_count, d_keys, d_payload, h->sm_count, s);
+    int count = 0;
+    cudaError_t e = cudaMemcpyAsync(&count, h->scratch_count, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && want) {
+        const size_t m = (size_t)std::min<int64_t>(count, capacity);
+        e = cudaMemcpy(keys, d_keys, m * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(payload, d_payload, m * BRICK_FLOATS * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    if (d_keys) cudaFree(d_keys);
+    if (d_payload) cudaFree(d_payload);
+    if (e != cudaSuccess) {
+        tsdf_set_error("export failed: %s", cudaGetErrorString(e));
+        return TSDF_ERR_CUDA;
+    }
+    *n = count;
+    return check_device_error(h);
+}
+
+extern "C" int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, int64_t *removed)
+{
+    BAD_ARG(!h || (!keys && n > 0), "NULL argument");
+    BAD_ARG(n < 0 || n > ((int64_t)1 << 30), "bad key count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->io.compute;
+    int count = 0;
+    if (n > 0) {
+        int32_t *d_keys = nullptr;
+        CUDA_TRY(cudaMalloc(&d_keys, (size_t)n * 3 * sizeof(int32_t)));
+        cudaError_t e = cudaMemcpyAsync(d_keys, keys, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(h->scratch_count, 0, sizeof(int), s);
+        launch_remove_blocks(h->dev, d_keys, (int)n, h->scratch_count, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&count, h->scratch_count, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_keys);
+        if (e != cudaSuccess) {
+            tsdf_set_error("remove failed: %s", cudaGetErrorString(e));
+            return TSDF_ERR_CUDA;
+        }
+    }
+    if (removed) *removed = count;
+    return TSDF_OK;
 }

@@ -10,7 +10,7 @@
 // Per frame:  prep_frame (fold colour, max depth)  ->  cull_bricks (frustum + depth range,
 // warp-aggregated compaction)  ->  integrate_bricks (persistent CTAs over the visible list).
 #include "launch.h"
-#include "tsdf_common.cuh"
+#include "integrate.cuh"
 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_fill_bricks(float4 *bricks, size_t n_float4)
@@ -66,108 +66,6 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
     }
 }
 
-// Per-thread body shared by the dense and the hash integrate kernels: geometry of four
-// z-consecutive voxels of one (x, y) column, then read-modify-write of their float4 per plane.
-//   cX/cY/cZ: the column's partial sums fma(T[r][1], wy, T[r][0]*wx); wz[4]: lattice z of the
-//   voxels; nvalid: how many of the four exist (z < dim_z).  rec: the float4 slot inside the brick
-//   record.  Returns the number of voxels updated.
-// Straight-line fast paths for 4 voxels (ILP), rare cases (IEEE-division pixel, band / general
-// weights) peeled off.  The voxel record is requested as soon as one voxel projects into the
-// image, together with the depth pixels, so the three dependent latencies (depth, record,
-// colour) overlap; the record bypasses L1 (streamed once per frame) so L1 keeps the depth /
-// colour pixels.
-template <bool UNIT_W>
-__device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double cX, double cY, double cZ,
-                                                   const double wz[4], int nvalid, float *rec)
-{
-    double Z[4], ax[4], ay[4];
-    int pix[4];
-    bool cand[4], exact[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pix[e], cand[e], exact[e]);
-        if (e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
-    }
-    if (exact[0] || exact[1] || exact[2] || exact[3]) { // ~2^-15 of the voxels
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (exact[e]) {
-                const int p = exact_pixel(ax[e], ay[e], Z[e], f.cx, f.cy, f.W, f.H);
-                if (p >= 0) { pix[e] = p; cand[e] = true; }
-            }
-    }
-    if (!(cand[0] || cand[1] || cand[2] || cand[3])) return 0;
-    // depth test (grid_fusion.py:278-286); record and colour requests ride along
-    double d[4];
-    uint32_t nc[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) d[e] = __ldg(f.depth + pix[e]);
-    const float4 T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
-    const float4 W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
-    const uint4 C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
-#pragma unroll
-    for (int e = 0; e < 4; ++e) nc[e] = __ldg(f.cfold + pix[e]);
-    double diff[4];
-    bool pass[4], band[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        diff[e] = __dadd_rn(d[e], -Z[e]);
-        pass[e] = cand[e] && d[e] > 0.0 && diff[e] >= f.neg_trunc;
-        band[e] = diff[e] < f.trunc;
-    }
-    if (!(pass[0] || pass[1] || pass[2] || pass[3])) return 0;
-    float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
-    uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
-    bool slow[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        float we = w[e];
-        uint32_t ce = c[e];
-        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, band[e], nc[e]);
-        if (pass[e] && ok) { w[e] = we; c[e] = ce; }
-        slow[e] = pass[e] && !ok;
-    }
-    if (slow[0] || slow[1] || slow[2] || slow[3]) { // truncation band, re-observed surface voxels, unusual obs_weight
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (slow[e]) {
-                // grid_fusion.py:286: min(1, diff/trunc); the quotient is >= 1 exactly when diff >= trunc
-                const double dist = band[e] ? fmin(1.0, __ddiv_rn(diff[e], f.trunc)) : 1.0;
-                Voxel vin;
-                vin.tsdf = t[e]; vin.wgt = w[e]; vin.col = c[e];
-                const Voxel vo = update_voxel_slow(vin, dist, nc[e], f.obs, f.obs_f);
-                t[e] = vo.tsdf; w[e] = vo.wgt; c[e] = vo.col;
-            }
-        __stcs(reinterpret_cast<float4 *>(rec), make_float4(t[0], t[1], t[2], t[3]));
-    }
-    __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), make_float4(w[0], w[1], w[2], w[3]));
-    __stcs(reinterpret_cast<uint4 *>(rec + 2 * BRICK_VOX), make_uint4(c[0], c[1], c[2], c[3]));
-    return (unsigned)pass[0] + (unsigned)pass[1] + (unsigned)pass[2] + (unsigned)pass[3];
-}
-
-// One (x, y) column of a brick: 8 voxels as two quads.  Returns the number of voxels updated.
-template <bool UNIT_W>
-__device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, const VolumeParams &v, int gx, int gy,
-                                                      int gz0, float *rec)
-{
-    const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
-    const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
-    const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
-    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
-    unsigned n = 0;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        const int gz = gz0 + 4 * h;
-        const int nvalid = v.dim_z - gz;
-        if (nvalid <= 0) break;
-        const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz));
-        const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz) + 1);
-        const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
-        n += integrate_quad<UNIT_W>(f, cX, cY, cZ, wz, nvalid, rec + 4 * h);
-    }
-    return n;
-}
-
 // Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
 // (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.  The next list entry is
 // fetched while the current brick is processed.
@@ -192,7 +90,7 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         }
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
-        my_updates += integrate_column8<UNIT_W>(f, v, gx, gy, br.z * BRICK,
+        my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
                                                 bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);

@@ -1,0 +1,417 @@
+// hash_kernels.cu -- sm_100a kernels of the voxel-block hash map (K2-K6 of SURVEY.md section 2a).
+//
+// Layout in HBM
+//   keys[S]    uint64  open-addressing table, S a power of two; key = bx<<42 | by<<21 | bz,
+//                      empty = all ones.  Slot = ((bx*P1) ^ (by*P2) ^ (bz*P3)) mod S with the
+//                      reference's primes (hash_fusion.py:24-26,182-190), linear probing.
+//   vals[S]    uint32  heap index of the block record, or NONE while the key has no storage
+//   entries[]  uint32  slots of all keys ever inserted (append-only), n_entries
+//   heap[H]    uint32  free list of block records, heap_top = number of free records
+//   blocks[H]  6 KB records, same format as the dense grid's bricks
+//
+// Per frame
+//   K2/K3 walk_insert   one warp per 8x8-pixel tile walks the tile's cone from the camera to
+//                       (max depth of the tile + trunc) in half-block steps and emits every block
+//                       the dilated sample touches; duplicates are removed inside the warp with
+//                       __match_any_sync, the leaders look the key up and insert it lock-free
+//                       (atomicCAS on the key word).  Keys only -- no storage yet.
+//   K4   compact        frustum/depth-range test of every table entry, warp ballot + prefix sum,
+//                       one atomic per warp -> visible block list
+//   K5   integrate      persistent CTAs, one block per iteration, the dense per-voxel rule.  A key
+//                       without storage is probed first (geometry only); storage is taken from the
+//                       free-list heap only if a voxel passes, so a block owns storage iff one of
+//                       its voxels has been updated == the reference's entry set, block-wise.
+#include "integrate.cuh"
+#include "launch.h"
+
+#define KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define VAL_NONE 0xFFFFFFFFu
+#define TILE_PX 8
+
+__device__ __forceinline__ unsigned long long pack_key(int bx, int by, int bz)
+{
+    return ((unsigned long long)bx << 42) | ((unsigned long long)by << 21) | (unsigned long long)bz;
+}
+__device__ __forceinline__ void unpack_key(unsigned long long k, int &bx, int &by, int &bz)
+{
+    bx = (int)(k >> 42);
+    by = (int)((k >> 21) & 0x1FFFFFull);
+    bz = (int)(k & 0x1FFFFFull);
+}
+// hash_fusion.py:182-190; for a power-of-two table the floor-mod is a mask
+__device__ __forceinline__ uint32_t slot_hash(int bx, int by, int bz, uint32_t mask)
+{
+    const long long h = ((long long)bx * 73856093LL) ^ ((long long)by * 19349669LL) ^ ((long long)bz * 83492791LL);
+    return (uint32_t)h & mask;
+}
+// shard owner: decorrelated from slot_hash (must match dist.block_owner in Python)
+__device__ __forceinline__ int owner_of(unsigned long long key, int world)
+{
+    return (int)(((key * 0x9E3779B97F4A7C15ull) >> 33) % (unsigned long long)world);
+}
+
+__device__ __forceinline__ void raise_error(Totals *tot, int code)
+{
+    atomicCAS(&tot->error, 0ull, (unsigned long long)(unsigned)(-code));
+}
+
+// Lookup; returns the slot or -1.
+__device__ __forceinline__ int table_find(const HashDev &h, unsigned long long key, int bx, int by, int bz)
+{
+    uint32_t slot = slot_hash(bx, by, bz, h.mask);
+    for (uint32_t probe = 0; probe <= h.mask; ++probe) {
+        const unsigned long long k = h.keys[slot];
+        if (k == key) return (int)slot;
+        if (k == KEY_EMPTY) return -1;
+        slot = (slot + 1) & h.mask;
+    }
+    return -1;
+}
+
+// Lock-free find-or-insert of a key (no storage).  atomicCAS on the 64-bit key word; the winner
+// appends the slot to the entry list.  Keys are never removed, so a key found once stays put.
+__device__ __forceinline__ void table_insert(const HashDev &h, unsigned long long key, int bx, int by, int bz,
+                                             FrameScratch *fs, Totals *tot)
+{
+    uint32_t slot = slot_hash(bx, by, bz, h.mask);
+    for (uint32_t probe = 0; probe <= h.mask; ++probe) {
+        unsigned long long k = h.keys[slot];
+        if (k == key) return;
+        if (k == KEY_EMPTY) {
+            k = atomicCAS(&h.keys[slot], KEY_EMPTY, key);
+            if (k == KEY_EMPTY) {
+                const int e = atomicAdd(h.n_entries, 1);
+                h.entries[e] = slot; // e < S because every slot is appended at most once
+                atomicAdd(&fs->new_keys, 1);
+                if (probe > 0) atomicMax(&tot->max_probe, (unsigned long long)probe);
+                return;
+            }
+            if (k == key) return; // another thread inserted the same key first
+        }
+        slot = (slot + 1) & h.mask;
+    }
+    raise_error(tot, TSDF_ERR_TABLE_FULL_CODE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Max valid depth per 8x8 pixel tile (0 = no valid pixel); one warp per tile.
+__global__ void k_tile_maxdepth(const double *__restrict__ depth, int H, int W, int tiles_x, int tiles_y,
+                                float *__restrict__ tile_dmax)
+{
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= tiles_x * tiles_y) return;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    float m = 0.0f;
+    for (int i = lane; i < TILE_PX * TILE_PX; i += 32) {
+        const int u = tx * TILE_PX + (i & 7), v = ty * TILE_PX + (i >> 3);
+        if (u < W && v < H) {
+            const double d = depth[v * W + u];
+            if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
+        }
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) tile_dmax[tile] = m;
+}
+
+// K2 + K3: cone walk per pixel tile, warp-aggregated dedup, lock-free insertion.
+__global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__ tile_dmax, FrameScratch *fs,
+                              Totals *tot)
+{
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= w.tiles_x * w.tiles_y) return;
+    const float dmax = tile_dmax[tile];
+    if (!(dmax > 0.0f)) return;
+    const int tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+    const int u0 = tx * TILE_PX, v0 = ty * TILE_PX;
+    const int u1 = min(u0 + TILE_PX, w.W) - 1, v1 = min(v0 + TILE_PX, w.H) - 1;
+    // centre ray of the tile and its lateral half-extent per unit depth (+0.51 px: pixel rounding)
+    const double dcx = (0.5 * (u0 + u1) - w.cx) / w.fx, dcy = (0.5 * (v0 + v1) - w.cy) / w.fy;
+    const double hx = (0.5 * (u1 - u0) + 0.51) / fabs(w.fx), hy = (0.5 * (v1 - v0) + 0.51) / fabs(w.fy);
+    const double lat = sqrt(hx * hx + hy * hy) * w.pose_scale;
+    // ray in voxel-index space: g(s) = e + s * d
+    const double dx = (w.P[0] * dcx + w.P[1] * dcy + w.P[2]) * w.inv_vs;
+    const double dy = (w.P[4] * dcx + w.P[5] * dcy + w.P[6]) * w.inv_vs;
+    const double dz = (w.P[8] * dcx + w.P[9] * dcy + w.P[10]) * w.inv_vs;
+    const double ex = (w.P[3] - w.ox) * w.inv_vs, ey = (w.P[7] - w.oy) * w.inv_vs, ez = (w.P[11] - w.oz) * w.inv_vs;
+    const double dlen = sqrt(dx * dx + dy * dy + dz * dz); // voxels of path per metre of depth
+    const double s_end = (double)dmax + w.trunc;
+    // clip [0, s_end] to the slab where the cone can touch the volume (index box dilated by the cone radius)
+    const double rmax = 0.5 * w.step * dlen + lat * w.inv_vs * (s_end + w.step) + 1.0;
+    double s0 = 0.0, s1 = s_end;
+    const double dd[3] = {dx, dy, dz}, ee[3] = {ex, ey, ez}, hi[3] = {(double)w.dim_x, (double)w.dim_y, (double)w.dim_z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double lo_b = -rmax - 1.0, hi_b = hi[a] + rmax;
+        if (fabs(dd[a]) < 1e-12) {
+            if (ee[a] < lo_b || ee[a] > hi_b) return;
+        } else {
+            double ta = (lo_b - ee[a]) / dd[a], tb = (hi_b - ee[a]) / dd[a];
+            if (ta > tb) { const double t = ta; ta = tb; tb = t; }
+            s0 = fmax(s0, ta);
+            s1 = fmin(s1, tb);
+        }
+    }
+    if (!(s0 <= s1)) return;
+    const int nsamp = (int)ceil((s1 - s0) / w.step) + 1;
+    for (int j = lane; j < nsamp; j += 32) {
+        const double s = fmin(s0 + j * w.step, s_end);
+        // every voxel centre a pixel of this tile can update at depth in [s - step/2, s + step/2]
+        // lies within rr voxels of the sample (along-ray half step + cone half width + slack)
+        const double rr = (0.5 * w.step * dlen + lat * w.inv_vs * (s + 0.5 * w.step)) * 1.001 + 0.02;
+        const double gx = ex + s * dx, gy = ey + s * dy, gz = ez + s * dz;
+        int ilo[3], ihi[3];
+        ilo[0] = max((int)ceil(gx - rr), 0); ihi[0] = min((int)floor(gx + rr), w.dim_x - 1);
+        ilo[1] = max((int)ceil(gy - rr), 0); ihi[1] = min((int)floor(gy + rr), w.dim_y - 1);
+        ilo[2] = max((int)ceil(gz - rr), 0); ihi[2] = min((int)floor(gz + rr), w.dim_z - 1);
+        if (ilo[0] > ihi[0] || ilo[1] > ihi[1] || ilo[2] > ihi[2]) continue;
+        for (int bx = ilo[0] >> 3; bx <= (ihi[0] >> 3); ++bx)
+            for (int by = ilo[1] >> 3; by <= (ihi[1] >> 3); ++by)
+                for (int bz = ilo[2] >> 3; bz <= (ihi[2] >> 3); ++bz) {
+                    const unsigned long long key = pack_key(bx, by, bz);
+                    // warp-aggregated dedup: lanes that emit the same key elect one leader
+                    const unsigned active = __activemask();
+                    const unsigned peers = __match_any_sync(active, key);
+                    if (lane != __ffs(peers) - 1) continue;
+                    if (h.world > 1 && owner_of(key, h.world) != h.rank) continue;
+                    atomicAdd(&fs->cand_count, 1);
+                    table_insert(h, key, bx, by, bz, fs, tot);
+                }
+    }
+}
+
+// K4: visible-block compaction over the entry list.
+__global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickRef *__restrict__ list, FrameScratch *fs)
+{
+    const int n = *h.n_entries;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i & ~31) >= n) return;
+    bool vis = false;
+    int bx = 0, by = 0, bz = 0;
+    uint32_t slot = 0;
+    if (i < n) {
+        slot = h.entries[i];
+        unpack_key(h.keys[slot], bx, by, bz);
+        c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+        vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, vis);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&fs->vis_count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (vis) {
+        BrickRef r;
+        r.bx = bx; r.by = by; r.bz = bz; r.storage = slot;
+        list[base + __popc(ballot & ((1u << lane) - 1u))] = r;
+    }
+}
+
+// K5: per-block integration.
+template <bool UNIT_W>
+__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
+k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__restrict__ list, FrameScratch *fs, Totals *tot)
+{
+    __shared__ uint32_t s_storage;
+    const int n = fs->vis_count;
+    const int t = threadIdx.x;
+    const int lx = t >> 3, ly = t & 7;
+    unsigned my_updates = 0;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int4 br = __ldg(reinterpret_cast<const int4 *>(list) + b);
+        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly, gz0 = br.z * BRICK;
+        const bool inb = gx < v.dim_x && gy < v.dim_y;
+        uint32_t storage = h.vals[(uint32_t)br.w]; // CTA-uniform
+        if (storage == VAL_NONE) {
+            // key without storage: geometry-only probe, allocate iff some voxel will be updated
+            const unsigned would = inb ? integrate_column8<UNIT_W, true>(f, v, gx, gy, gz0, nullptr) : 0u;
+            if (!__syncthreads_or(would != 0u)) continue;
+            if (t == 0) {
+                const int top = atomicSub(h.heap_top, 1) - 1; // atomic free-list pop
+                uint32_t blk = VAL_NONE;
+                if (top >= 0) {
+                    blk = h.heap[top];
+                    h.vals[(uint32_t)br.w] = blk;
+                } else {
+                    atomicAdd(h.heap_top, 1);
+                    raise_error(tot, TSDF_ERR_HEAP_EXHAUSTED_CODE);
+                }
+                s_storage = blk;
+            }
+            __syncthreads();
+            storage = s_storage;
+            if (storage == VAL_NONE) continue;
+            // initialise the record: tsdf = 1, weight = 0, colour = 0 (voxel.py:8)
+            float *rec = h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t;
+            const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            __stcs(reinterpret_cast<float4 *>(rec), one);
+            __stcs(reinterpret_cast<float4 *>(rec) + 1, one);
+            __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), zero);
+            __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX) + 1, zero);
+            __stcs(reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX), zero);
+            __stcs(reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX) + 1, zero);
+        }
+        if (inb)
+            my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, gz0,
+                                                           h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t);
+    }
+    for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
+    if ((t & 31) == 0 && my_updates) {
+        atomicAdd(&fs->updated, (unsigned long long)my_updates);
+        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    }
+    if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table initialisation: keys = EMPTY, vals = NONE, heap[i] = H-1-i (record 0 is handed out first).
+__global__ void k_hash_init(HashDev h)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i <= h.mask; i += stride) {
+        h.keys[i] = KEY_EMPTY;
+        h.vals[i] = VAL_NONE;
+    }
+    for (size_t i = i0; i < (size_t)h.heap_cap; i += stride) h.heap[i] = (uint32_t)(h.heap_cap - 1 - i);
+    if (i0 == 0) {
+        *h.n_entries = 0;
+        *h.heap_top = h.heap_cap;
+    }
+}
+
+__global__ void k_fill_dense(float *tsdf, float *wgt, float *col, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (tsdf) tsdf[i] = 1.0f;
+        if (wgt) wgt[i] = 0.0f;
+        if (col) col[i] = 0.0f;
+    }
+}
+
+// K6: scatter every block that owns storage into dense [X][Y][Z] volumes (hash_fusion.py:442-463).
+__global__ void k_scatter_dense(HashDev h, int dim_x, int dim_y, int dim_z, float *tsdf, float *wgt, float *col)
+{
+    const int n = *h.n_entries;
+    const int t = threadIdx.x, lx = t >> 3, ly = t & 7;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t slot = h.entries[e];
+        const uint32_t storage = h.vals[slot];
+        if (storage == VAL_NONE) continue;
+        int bx, by, bz;
+        unpack_key(h.keys[slot], bx, by, bz);
+        const int gx = bx * BRICK + lx, gy = by * BRICK + ly;
+        if (gx >= dim_x || gy >= dim_y) continue;
+        const float *rec = h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t;
+        const size_t base = ((size_t)gx * dim_y + gy) * dim_z + (size_t)bz * BRICK;
+        for (int k = 0; k < BRICK && bz * BRICK + k < dim_z; ++k) {
+            if (tsdf) tsdf[base + k] = rec[k];
+            if (wgt) wgt[base + k] = rec[BRICK_VOX + k];
+            if (col) col[base + k] = (float)__float_as_uint(rec[2 * BRICK_VOX + k]);
+        }
+    }
+}
+
+// Block export: compacts the blocks that own storage; colour converted to the float encoding.
+__global__ void k_export_blocks(HashDev h, int capacity, int *count, int32_t *keys_out, float *payload)
+{
+    __shared__ int s_idx;
+    const int n = *h.n_entries;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t slot = h.entries[e];
+        const uint32_t storage = h.vals[slot];
+        if (storage == VAL_NONE) continue; // CTA-uniform
+        if (threadIdx.x == 0) s_idx = atomicAdd(count, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        __syncthreads();
+        if (idx >= capacity || !keys_out || !payload) continue;
+        if (threadIdx.x == 0) {
+            int bx, by, bz;
+            unpack_key(h.keys[slot], bx, by, bz);
+            keys_out[3 * idx] = bx; keys_out[3 * idx + 1] = by; keys_out[3 * idx + 2] = bz;
+        }
+        const float *rec = h.blocks + (size_t)storage * BRICK_FLOATS;
+        float *dst = payload + (size_t)idx * BRICK_FLOATS;
+        for (int i = threadIdx.x; i < BRICK_FLOATS; i += blockDim.x)
+            dst[i] = i < 2 * BRICK_VOX ? rec[i] : (float)__float_as_uint(rec[i]);
+    }
+}
+
+// Block removal (hash_fusion.py:322-393 at block granularity): the record returns to the free
+// list (atomic push); the key stays in the table without storage, so probe chains never break.
+__global__ void k_remove_blocks(HashDev h, const int32_t *keys, int n, int *removed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int bx = keys[3 * i], by = keys[3 * i + 1], bz = keys[3 * i + 2];
+    if (bx < 0 || by < 0 || bz < 0 || bx >= (1 << 21) || by >= (1 << 21) || bz >= (1 << 21)) return;
+    const int slot = table_find(h, pack_key(bx, by, bz), bx, by, bz);
+    if (slot < 0) return;
+    const uint32_t storage = atomicExch(&h.vals[slot], VAL_NONE); // duplicates in `keys` free it once
+    if (storage == VAL_NONE) return;
+    h.heap[atomicAdd(h.heap_top, 1)] = storage;
+    atomicAdd(removed, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s) { k_hash_init<<<sm_count * 4, 256, 0, s>>>(h); }
+
+void launch_tile_maxdepth(const double *depth, int H, int W, int tiles_x, int tiles_y, float *tile_dmax, cudaStream_t s)
+{
+    const int warps = tiles_x * tiles_y;
+    k_tile_maxdepth<<<(warps * 32 + 255) / 256, 256, 0, s>>>(depth, H, W, tiles_x, tiles_y, tile_dmax);
+}
+
+void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
+                        cudaStream_t s)
+{
+    const int warps = w.tiles_x * w.tiles_y;
+    k_walk_insert<<<(warps * 32 + 127) / 128, 128, 0, s>>>(w, h, tile_dmax, fs, tot);
+}
+
+void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
+                            BrickRef *list, FrameScratch *fs, cudaStream_t s)
+{
+    if (max_entries <= 0) return;
+    k_compact_visible<<<(max_entries + 255) / 256, 256, 0, s>>>(f, c, h, list, fs);
+}
+
+int integrate_hash_ctas_per_sm()
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_hash<true>, INTEGRATE_THREADS, 0);
+    return n > 0 ? n : 1;
+}
+
+void launch_integrate_hash(const FrameParams &f, const VolumeParams &v, const HashDev &h, const BrickRef *list,
+                           FrameScratch *fs, Totals *tot, int grid, cudaStream_t s)
+{
+    if (f.unit_w)
+        k_integrate_hash<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot);
+    else
+        k_integrate_hash<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot);
+}
+
+void launch_scatter_dense(const HashDev &h, int dim_x, int dim_y, int dim_z, float *tsdf, float *wgt, float *col,
+                          int sm_count, cudaStream_t s)
+{
+    const size_t n = (size_t)dim_x * dim_y * dim_z;
+    k_fill_dense<<<sm_count * 8, 256, 0, s>>>(tsdf, wgt, col, n);
+    k_scatter_dense<<<sm_count * 16, INTEGRATE_THREADS, 0, s>>>(h, dim_x, dim_y, dim_z, tsdf, wgt, col);
+}
+
+void launch_export_blocks(const HashDev &h, int capacity, int *count, int32_t *keys_out, float *payload, int sm_count,
+                          cudaStream_t s)
+{
+    k_export_blocks<<<sm_count * 8, 128, 0, s>>>(h, capacity, count, keys_out, payload);
+}
+
+void launch_remove_blocks(const HashDev &h, const int32_t *keys, int n, int *removed, cudaStream_t s)
+{
+    if (n <= 0) return;
+    k_remove_blocks<<<(n + 255) / 256, 256, 0, s>>>(h, keys, n, removed);
+}

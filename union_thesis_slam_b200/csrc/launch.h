@@ -37,3 +37,48 @@ void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const B
                             FrameScratch *fs, Totals *tot, int grid, cudaStream_t s);
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
                     float *col, int sm_count, cudaStream_t s);
+
+// ---- voxel-block hash map -----------------------------------------------------------------------
+#define TSDF_ERR_HEAP_EXHAUSTED_CODE (-5)
+#define TSDF_ERR_TABLE_FULL_CODE (-6)
+
+struct HashDev {
+    unsigned long long *keys; // [mask + 1]
+    uint32_t *vals;           // [mask + 1] heap index or NONE
+    uint32_t mask;
+    uint32_t *entries;        // [mask + 1] slots of inserted keys
+    int *n_entries;
+    uint32_t *heap;           // [heap_cap] free block records
+    int *heap_top;            // number of free records
+    int heap_cap;
+    float *blocks;            // [heap_cap][1536]
+    int rank, world;
+};
+
+// Ray-walk constants of one frame (forward pose = inverse of Tinv, computed on the host).
+struct WalkParams {
+    double P[12];             // camera -> world, rows 0..2
+    double ox, oy, oz;        // volume origin
+    double inv_vs;            // 1 / voxel size
+    double step;              // sample spacing in metres of z-depth
+    double trunc;
+    double fx, fy, cx, cy;
+    double pose_scale;        // upper bound of the 2-norm of the pose's 3x3 block
+    int W, H, tiles_x, tiles_y;
+    int dim_x, dim_y, dim_z;
+};
+
+void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s);
+void launch_tile_maxdepth(const double *depth, int H, int W, int tiles_x, int tiles_y, float *tile_dmax, cudaStream_t s);
+void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
+                        cudaStream_t s);
+void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
+                            BrickRef *list, FrameScratch *fs, cudaStream_t s);
+int integrate_hash_ctas_per_sm();
+void launch_integrate_hash(const FrameParams &f, const VolumeParams &v, const HashDev &h, const BrickRef *list,
+                           FrameScratch *fs, Totals *tot, int grid, cudaStream_t s);
+void launch_scatter_dense(const HashDev &h, int dim_x, int dim_y, int dim_z, float *tsdf, float *wgt, float *col,
+                          int sm_count, cudaStream_t s);
+void launch_export_blocks(const HashDev &h, int capacity, int *count, int32_t *keys_out, float *payload, int sm_count,
+                          cudaStream_t s);
+void launch_remove_blocks(const HashDev &h, const int32_t *keys, int n, int *removed, cudaStream_t s);
