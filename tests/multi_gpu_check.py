@@ -1,0 +1,59 @@
+"""Multi-GPU parity check, launched with torchrun on a box with >= 2 GPUs (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_check.py
+
+Every rank integrates the same frames into its shard (cyclic x-sheets / owner-hashed blocks, no
+per-frame collective); get_volume() gathers over NCCL and must equal the CPU oracle bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import scenes  # noqa: E402
+from oracle import oracle  # noqa: E402
+from union_thesis_slam_b200 import grid_fusion, hash_fusion  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    case = scenes.small_case(301, dims=(70, 40, 44), voxel_size=0.02, nframes=3)
+    vol = grid_fusion.TSDFVolume(case["vol_bnds"].copy(), 0.02)      # rank/world from the process group
+    ht = hash_fusion.HashTable(case["vol_bnds"].copy(), 0.02, map_size=1 << 14)
+    assert (vol.rank, vol.world_size, vol.device) == (rank, world, local)
+    orc = oracle.OracleTSDFVolume(case["vol_bnds"].copy(), 0.02)
+    for c, d, p, obs in case["frames"]:
+        vol.integrate(c, d, case["K"], p, obs_weight=obs)
+        ht.integrate(c, d, case["K"], p, obs_weight=obs)
+        orc.integrate(c, d, case["K"], p, obs_weight=obs)
+    t, c_ = vol.get_volume()
+    w = vol._weight_vol_cpu
+    ok = (np.array_equal(t, orc._tsdf_vol_cpu) and np.array_equal(w, orc._weight_vol_cpu)
+          and np.array_equal(c_, orc._color_vol_cpu))
+    ht_t, ht_w, ht_c = ht.get_volume_with_weight()
+    ok_h = np.array_equal(ht_t, t) and np.array_equal(ht_w, w) and np.array_equal(ht_c, c_)
+    nblk = torch.tensor([ht.stats()["blocks"]], device="cuda")
+    dist.all_reduce(nblk)
+    want = len(oracle.block_set_from_weight(orc._weight_vol_cpu))
+    flag = torch.tensor([int(ok and ok_h and int(nblk.item()) == want)], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("multi_gpu_check world=%d dense=%s hash=%s blocks=%d/%d -> %s" % (
+            world, ok, ok_h, int(nblk.item()), want, "OK" if flag.item() == 1 else "FAIL"))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if flag.item() == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

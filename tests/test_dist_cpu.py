@@ -1,0 +1,102 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo process groups (-m "not gpu").
+
+The kernels need no per-frame collective; what is distributed is (1) the ownership maps and
+(2) the read-out gather/merge, which are exercised here over gloo with the CPU oracle standing
+in for the per-rank shards (the oracle accepts the same x-sheet subsets).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import frames
+from oracle import oracle
+from union_thesis_slam_b200 import dist as tdist
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn, world=2):
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+def test_owned_x_is_a_partition_with_brick_thick_cyclic_sheets():
+    for dim_x, world in [(405, 2), (405, 8), (1000, 4), (7, 3), (64, 8)]:
+        seen = np.zeros(dim_x, int)
+        for r in range(world):
+            xs = tdist.owned_x(dim_x, r, world)
+            assert np.all((xs // 8) % world == r) and np.all(np.diff(xs) > 0)
+            seen[xs] += 1
+        assert np.all(seen == 1)
+
+
+def test_block_owner_is_balanced_and_decorrelated_from_slot_hash():
+    g = np.stack(np.meshgrid(np.arange(51), np.arange(33), np.arange(37), indexing="ij"), -1).reshape(-1, 3)
+    for world in (2, 4, 8):
+        own = tdist.block_owner(g, world)
+        counts = np.bincount(own, minlength=world)
+        assert counts.min() > 0.9 * len(g) / world and counts.max() < 1.1 * len(g) / world
+        # with owner = slot_hash % P the keys of one rank use 1/P of a 2^k table
+        slot = ((g[:, 0] * 73856093) ^ (g[:, 1] * 19349669) ^ (g[:, 2] * 83492791)) % 65536
+        mine = slot[own == 0]
+        assert len(np.unique(mine % world)) == world
+
+
+def _gather_job(rank, world):
+    z = np.load(os.path.join(frames.GOLDEN_DIR, "small_dense_12.npz"))
+    X = z["tsdf"].shape[0]
+    xs = tdist.owned_x(X, rank, world)
+    vol = oracle.OracleTSDFVolume(z["vol_bnds"].copy(), float(z["voxel_size"]), xs=xs)
+    for i in range(len(z["obs"])):
+        vol.integrate(z["color"][i], z["depth"][i], z["K"], z["pose"][i], obs_weight=float(z["obs"][i]))
+    out = []
+    for plane, ref in ((vol._tsdf_vol_cpu, z["tsdf"]), (vol._weight_vol_cpu, z["weight"]),
+                       (vol._color_vol_cpu, z["color_vol"])):
+        full = tdist.gather_x_sheets(torch.from_numpy(plane), X, rank, world).numpy()
+        out.append(bool(np.array_equal(full, ref)))
+    assert tdist.rank_world() == (rank, world)
+    return out
+
+
+def test_x_sheet_gather_reconstructs_the_reference_volume_world2():
+    res = _spawn(_gather_job, 2)
+    assert res == {0: [True, True, True], 1: [True, True, True]}
+
+
+def test_x_sheet_gather_world3_uneven_sheets():
+    res = _spawn(_gather_job, 3)  # 33 rows -> 5 sheets: ranks own 2/2/1 sheets, the last one partial
+    assert all(all(v) for v in res.values()) and len(res) == 3
+
+
+def _merge_job(rank, world):
+    z = np.load(os.path.join(frames.GOLDEN_DIR, "small_dense_11.npz"))
+    t, w, c = z["tsdf"], z["weight"], z["color_vol"]
+    idx = np.stack(np.meshgrid(*[np.arange(s) for s in t.shape], indexing="ij"), -1)
+    mine = tdist.block_owner(idx // 8, world) == rank
+    lt = np.where(mine, t, 1.0).astype(np.float32)
+    lw = np.where(mine, w, 0.0).astype(np.float32)
+    lc = np.where(mine, c, 0.0).astype(np.float32)
+    mt, mw, mc = tdist.merge_disjoint_volumes(torch.from_numpy(lt), torch.from_numpy(lw), torch.from_numpy(lc))
+    return [bool(np.array_equal(mt.numpy(), t)), bool(np.array_equal(mw.numpy(), w)), bool(np.array_equal(mc.numpy(), c))]
+
+
+def test_hash_shard_merge_is_bit_exact_world2():
+    res = _spawn(_merge_job, 2)
+    assert res == {0: [True, True, True], 1: [True, True, True]}
