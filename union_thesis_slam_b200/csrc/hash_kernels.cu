@@ -155,6 +155,7 @@ __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__
     }
     if (!(s0 <= s1)) return;
     const int nsamp = (int)ceil((s1 - s0) / w.step) + 1;
+    int my_cand = 0;
     for (int j = lane; j < nsamp; j += 32) {
         const double s = fmin(s0 + j * w.step, s_end);
         // every voxel centre a pixel of this tile can update at depth in [s - step/2, s + step/2]
@@ -175,10 +176,14 @@ __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__
                     const unsigned peers = __match_any_sync(active, key);
                     if (lane != __ffs(peers) - 1) continue;
                     if (h.world > 1 && owner_of(key, h.world) != h.rank) continue;
-                    atomicAdd(&fs->cand_count, 1);
+                    ++my_cand;
                     table_insert(h, key, bx, by, bz, fs, tot);
                 }
     }
+    // one counter update per warp (a per-candidate atomic on one address serialises the kernel)
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) my_cand += __shfl_xor_sync(0xffffffffu, my_cand, o);
+    if (lane == 0 && my_cand) atomicAdd(&fs->cand_count, my_cand);
 }
 
 // K4: visible-block compaction over the entry list.
