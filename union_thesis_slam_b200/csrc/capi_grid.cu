@@ -177,6 +177,39 @@ int FrameIO::ensure(int npix)
     return TSDF_OK;
 }
 
+int FrameIO::ensure_tiles(int H, int W)
+{
+    if (d_scratch && H == tiles_H && W == tiles_W) return TSDF_OK;
+    CUDA_TRY(cudaStreamSynchronize(compute));
+    if (d_scratch) cudaFree(d_scratch);
+    d_scratch = nullptr;
+    size_t off[4], total = 256; // FrameScratch lives in the first 256 bytes
+    for (int l = 1; l <= 3; ++l) {
+        pyr.tx[l] = (W + (8 << l) - 1) / (8 << l);
+        pyr.ty[l] = (H + (8 << l) - 1) / (8 << l);
+        off[l] = total;
+        total += (((size_t)pyr.tx[l] * pyr.ty[l] * sizeof(float)) + 255) / 256 * 256;
+    }
+    clear_bytes = total;
+    pyr.tx[0] = (W + 7) / 8;
+    pyr.ty[0] = (H + 7) / 8;
+    off[0] = total;
+    total += (size_t)pyr.tx[0] * pyr.ty[0] * sizeof(float);
+    CUDA_TRY(cudaMalloc(&d_scratch, total));
+    CUDA_TRY(cudaMemsetAsync(d_scratch, 0, total, compute));
+    fs = reinterpret_cast<FrameScratch *>(d_scratch);
+    for (int l = 0; l < 4; ++l) pyr.level[l] = reinterpret_cast<float *>(d_scratch + off[l]);
+    tiles_H = H;
+    tiles_W = W;
+    return TSDF_OK;
+}
+
+int FrameIO::clear_scratch()
+{
+    CUDA_TRY(cudaMemsetAsync(d_scratch, 0, clear_bytes, compute));
+    return TSDF_OK;
+}
+
 static bool is_pinned_host(const void *p)
 {
     cudaPointerAttributes a;
@@ -318,7 +351,6 @@ struct tsdf_grid {
     size_t nbricks = 0;
     float *bricks = nullptr;
     BrickRef *vis_list = nullptr;
-    FrameScratch *fs = nullptr;
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
@@ -334,7 +366,6 @@ static int grid_free(tsdf_grid *g)
     g->geom.release();
     if (g->bricks) cudaFree(g->bricks);
     if (g->vis_list) cudaFree(g->vis_list);
-    if (g->fs) cudaFree(g->fs);
     if (g->tot) cudaFree(g->tot);
     delete g;
     return TSDF_OK;
@@ -376,14 +407,12 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
     if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&g->vis_list, nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&g->fs, sizeof(FrameScratch))) != cudaSuccess ||
         (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
         cudaGetLastError();
         grid_free(g);
         return TSDF_ERR_OOM;
     }
-    cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), g->io.compute);
     cudaMemsetAsync(g->tot, 0, sizeof(Totals), g->io.compute);
     launch_fill_bricks(g->bricks, g->nbricks, sm, g->io.compute);
     g->integrate_grid = sm * integrate_dense_ctas_per_sm();
@@ -403,18 +432,19 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
                     CullParams &c)
 {
     int rc = g->io.ensure_cfold(H * W);
-    if (rc) return rc;
+    if (rc || (rc = g->io.ensure_tiles(H, W))) return rc;
     cudaStream_t s = g->io.compute;
+    c.pyr = g->io.pyr;
     f.depth = d_depth;
     f.cfold = g->io.d_cfold;
     g->unit_w = g->unit_w && f.obs == 1.0;
     f.unit_w = g->unit_w ? 1 : 0;
     if ((rc = g->io.begin_kernels())) return rc;
-    CUDA_TRY(cudaMemsetAsync(g->fs, 0, sizeof(FrameScratch), s));
-    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->fs, H * W, g->sm_count, s);
-    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->vis_list, g->fs, s);
+    if ((rc = g->io.clear_scratch())) return rc;
+    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, s);
+    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->vis_list, g->io.fs, s);
     if (g->profile_stages && (rc = g->io.mark())) return rc;
-    launch_integrate_dense(f, g->geom.params(), g->vis_list, g->bricks, g->fs, g->tot, g->integrate_grid, s);
+    launch_integrate_dense(f, g->geom.params(), g->vis_list, g->bricks, g->io.fs, g->tot, g->integrate_grid, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
     g->frames++;
@@ -506,8 +536,9 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
     CUDA_TRY(cudaSetDevice(g->device));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));
     FrameScratch fs;
+    memset(&fs, 0, sizeof(fs));
     Totals tot;
-    CUDA_TRY(cudaMemcpy(&fs, g->fs, sizeof(fs), cudaMemcpyDeviceToHost));
+    if (g->io.fs) CUDA_TRY(cudaMemcpy(&fs, g->io.fs, sizeof(fs), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&tot, g->tot, sizeof(tot), cudaMemcpyDeviceToHost));
     counters[0] = (int64_t)fs.updated;
     counters[1] = (int64_t)tot.updated;

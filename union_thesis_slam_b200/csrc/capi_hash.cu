@@ -12,10 +12,7 @@ struct tsdf_hash {
     HashDev dev{};
     int64_t table_slots = 0, heap_blocks = 0;
     BrickRef *vis_list = nullptr;
-    FrameScratch *fs = nullptr;
     Totals *tot = nullptr;
-    float *tile_dmax = nullptr;
-    int tile_cap = 0;
     int *scratch_count = nullptr; // device int used by export / remove
     int integrate_grid = 0;
     int64_t frames = 0;
@@ -30,7 +27,7 @@ static int hash_free(tsdf_hash *h)
     h->io.release();
     h->geom.release();
     void *ptrs[] = {h->dev.keys, h->dev.vals, h->dev.entries, h->dev.n_entries, h->dev.heap, h->dev.heap_top,
-                    h->dev.blocks, h->vis_list, h->fs, h->tot, h->tile_dmax, h->scratch_count};
+                    h->dev.blocks, h->vis_list, h->tot, h->scratch_count};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -82,7 +79,6 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         (e = cudaMalloc(&d.heap_top, sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&h->vis_list, S * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&h->fs, sizeof(FrameScratch))) != cudaSuccess ||
         (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
         (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
         tsdf_set_error("device allocation failed (%lld slots, %lld blocks = %.2f GB): %s", (long long)S,
@@ -91,7 +87,6 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         hash_free(h);
         return TSDF_ERR_OOM;
     }
-    cudaMemsetAsync(h->fs, 0, sizeof(FrameScratch), h->io.compute);
     cudaMemsetAsync(h->tot, 0, sizeof(Totals), h->io.compute);
     launch_hash_init(d, sm, h->io.compute);
     h->integrate_grid = sm * integrate_hash_ctas_per_sm();
@@ -143,16 +138,10 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
                     CullParams &c, const double Tinv[16])
 {
     int rc = h->io.ensure_cfold(H * W);
-    if (rc) return rc;
+    if (rc || (rc = h->io.ensure_tiles(H, W))) return rc;
     cudaStream_t s = h->io.compute;
-    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
-    if (tiles_x * tiles_y > h->tile_cap) {
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (h->tile_dmax) cudaFree(h->tile_dmax);
-        h->tile_dmax = nullptr;
-        CUDA_TRY(cudaMalloc(&h->tile_dmax, (size_t)tiles_x * tiles_y * sizeof(float)));
-        h->tile_cap = tiles_x * tiles_y;
-    }
+    c.pyr = h->io.pyr;
+    const int tiles_x = h->io.pyr.tx[0], tiles_y = h->io.pyr.ty[0];
     WalkParams w;
     BAD_ARG(invert_affine(Tinv, w.P) != 0, "Tinv is singular");
     w.ox = (double)h->geom.origin[0]; w.oy = (double)h->geom.origin[1]; w.oz = (double)h->geom.origin[2];
@@ -172,6 +161,12 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
         }
     w.pose_scale = sqrt(1.0 + sqrt(ef)) * 1.000001;
     w.W = W; w.H = H; w.tiles_x = tiles_x; w.tiles_y = tiles_y;
+    {   // a ray is inside the (dilated) volume for at most its diagonal: bound the samples per tile
+        double diag = 0.0;
+        for (int a = 0; a < 3; ++a) diag += (double)h->geom.dim[a] * h->geom.dim[a];
+        const double max_samples = (sqrt(diag) + 64.0) * h->geom.vs / w.step * 1.5 + 4.0;
+        w.chunks = std::max(1, std::min(64, (int)ceil(max_samples / 32.0)));
+    }
     w.dim_x = (int)h->geom.dim[0]; w.dim_y = (int)h->geom.dim[1]; w.dim_z = (int)h->geom.dim[2];
 
     f.depth = d_depth;
@@ -179,12 +174,11 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     h->unit_w = h->unit_w && f.obs == 1.0;
     f.unit_w = h->unit_w ? 1 : 0;
     if ((rc = h->io.begin_kernels())) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->fs, 0, sizeof(FrameScratch), s));
-    launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->fs, H * W, h->sm_count, s);
-    launch_tile_maxdepth(d_depth, H, W, tiles_x, tiles_y, h->tile_dmax, s);
-    launch_walk_insert(w, h->dev, h->tile_dmax, h->fs, h->tot, s);
-    launch_compact_visible(f, c, h->dev, (int)h->table_slots, h->vis_list, h->fs, s);
-    launch_integrate_hash(f, h->geom.params(), h->dev, h->vis_list, h->fs, h->tot, h->integrate_grid, s);
+    if ((rc = h->io.clear_scratch())) return rc;
+    launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->io.fs, h->io.pyr, H, W, s);
+    launch_walk_insert(w, h->dev, h->io.pyr.level[0], h->io.fs, h->tot, s);
+    launch_compact_visible(f, c, h->dev, (int)h->table_slots, h->vis_list, h->io.fs, s);
+    launch_integrate_hash(f, h->geom.params(), h->dev, h->vis_list, h->io.fs, h->tot, h->integrate_grid, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.end_kernels())) return rc;
     h->frames++;
@@ -224,9 +218,10 @@ extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->io.compute));
     FrameScratch fs;
+    memset(&fs, 0, sizeof(fs));
     Totals tot;
     int n_entries = 0, heap_top = 0;
-    CUDA_TRY(cudaMemcpy(&fs, h->fs, sizeof(fs), cudaMemcpyDeviceToHost));
+    if (h->io.fs) CUDA_TRY(cudaMemcpy(&fs, h->io.fs, sizeof(fs), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&tot, h->tot, sizeof(tot), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&n_entries, h->dev.n_entries, sizeof(int), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&heap_top, h->dev.heap_top, sizeof(int), cudaMemcpyDeviceToHost));

@@ -23,19 +23,39 @@ __global__ void k_fill_bricks(float4 *bricks, size_t n_float4)
     }
 }
 
-// grid_fusion.py:228-232 colour fold (as an exact integer) + max valid depth of the frame.
+// grid_fusion.py:228-232 colour fold (as an exact integer), max valid depth of the frame and the
+// per-tile max-depth pyramid.  One warp per 8x8-pixel tile, two horizontally adjacent pixels per lane.
 __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__restrict__ depth,
-                             uint32_t *__restrict__ cfold, FrameScratch *fs, int npix)
+                             uint32_t *__restrict__ cfold, FrameScratch *fs, TilePyramid pyr, int H, int W)
 {
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= pyr.tx[0] * pyr.ty[0]) return;
+    const int tx = tile % pyr.tx[0], ty = tile / pyr.tx[0];
+    const int v = ty * 8 + (lane >> 2), u = tx * 8 + (lane & 3) * 2;
     float m = 0.0f;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
-        const uint32_t r = rgb[3 * p], g = rgb[3 * p + 1], b = rgb[3 * p + 2];
-        cfold[p] = (b << 16) | (g << 8) | r;
-        const double d = depth[p];
-        if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
+    if (v < H) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (u + k < W) {
+                const int p = v * W + u + k;
+                const uint32_t r = __ldg(rgb + 3 * p), g = __ldg(rgb + 3 * p + 1), b = __ldg(rgb + 3 * p + 2);
+                cfold[p] = (b << 16) | (g << 8) | r;
+                const double d = __ldg(depth + p);
+                if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
+            }
     }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&fs->max_depth_bits, __float_as_uint(m));
+    if (lane == 0) {
+        pyr.level[0][tile] = m;
+        if (m > 0.0f) {
+            const unsigned bits = __float_as_uint(m);
+            atomicMax(reinterpret_cast<unsigned *>(pyr.level[1]) + (ty >> 1) * pyr.tx[1] + (tx >> 1), bits);
+            atomicMax(reinterpret_cast<unsigned *>(pyr.level[2]) + (ty >> 2) * pyr.tx[2] + (tx >> 2), bits);
+            atomicMax(reinterpret_cast<unsigned *>(pyr.level[3]) + (ty >> 3) * pyr.tx[3] + (tx >> 3), bits);
+            atomicMax(&fs->max_depth_bits, bits);
+        }
+    }
 }
 
 // One thread per local brick; visible bricks are appended with one atomic per warp.
@@ -128,12 +148,11 @@ void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_
     k_fill_bricks<<<sm_count * 8, 256, 0, s>>>(reinterpret_cast<float4 *>(bricks), n4);
 }
 
-void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs, int npix,
-                       int sm_count, cudaStream_t s)
+void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
+                       const TilePyramid &pyr, int H, int W, cudaStream_t s)
 {
-    int blocks = (npix + 255) / 256;
-    if (blocks > sm_count * 8) blocks = sm_count * 8;
-    k_prep_frame<<<blocks, 256, 0, s>>>(rgb, depth, cfold, fs, npix);
+    const int warps = pyr.tx[0] * pyr.ty[0];
+    k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, cfold, fs, pyr, H, W);
 }
 
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,

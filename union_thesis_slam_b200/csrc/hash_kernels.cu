@@ -10,6 +10,7 @@
 //   blocks[H]  6 KB records, same format as the dense grid's bricks
 //
 // Per frame
+//   (prep_frame builds the per-tile max-depth pyramid, dense_kernels.cu)
 //   K2/K3 walk_insert   one warp per 8x8-pixel tile walks the tile's cone from the camera to
 //                       (max depth of the tile + trunc) in half-block steps and emits every block
 //                       the dilated sample touches; duplicates are removed inside the warp with
@@ -94,32 +95,15 @@ __device__ __forceinline__ void table_insert(const HashDev &h, unsigned long lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// Max valid depth per 8x8 pixel tile (0 = no valid pixel); one warp per tile.
-__global__ void k_tile_maxdepth(const double *__restrict__ depth, int H, int W, int tiles_x, int tiles_y,
-                                float *__restrict__ tile_dmax)
-{
-    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (tile >= tiles_x * tiles_y) return;
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-    float m = 0.0f;
-    for (int i = lane; i < TILE_PX * TILE_PX; i += 32) {
-        const int u = tx * TILE_PX + (i & 7), v = ty * TILE_PX + (i >> 3);
-        if (u < W && v < H) {
-            const double d = depth[v * W + u];
-            if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
-        }
-    }
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) tile_dmax[tile] = m;
-}
-
 // K2 + K3: cone walk per pixel tile, warp-aggregated dedup, lock-free insertion.
 __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__ tile_dmax, FrameScratch *fs,
                               Totals *tot)
 {
-    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // one warp per (tile, chunk of 32 consecutive samples): many short independent walks instead
+    // of few long ones, so the table probes of different chunks overlap
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const int tile = warp / w.chunks, chunk = warp - tile * w.chunks;
     if (tile >= w.tiles_x * w.tiles_y) return;
     const float dmax = tile_dmax[tile];
     if (!(dmax > 0.0f)) return;
@@ -156,7 +140,9 @@ __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__
     if (!(s0 <= s1)) return;
     const int nsamp = (int)ceil((s1 - s0) / w.step) + 1;
     int my_cand = 0;
-    for (int j = lane; j < nsamp; j += 32) {
+    // chunks beyond w.chunks - 1 (never needed when the host bound holds) fold into the last one
+    const int j_end = (chunk == w.chunks - 1) ? nsamp : min(nsamp, (chunk + 1) * 32);
+    for (int j = chunk * 32 + lane; j < j_end; j += 32) {
         const double s = fmin(s0 + j * w.step, s_end);
         // every voxel centre a pixel of this tile can update at depth in [s - step/2, s + step/2]
         // lies within rr voxels of the sample (along-ray half step + cone half width + slack)
@@ -365,17 +351,11 @@ __global__ void k_remove_blocks(HashDev h, const int32_t *keys, int n, int *remo
 // ---------------------------------------------------------------------------------------------
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s) { k_hash_init<<<sm_count * 4, 256, 0, s>>>(h); }
 
-void launch_tile_maxdepth(const double *depth, int H, int W, int tiles_x, int tiles_y, float *tile_dmax, cudaStream_t s)
-{
-    const int warps = tiles_x * tiles_y;
-    k_tile_maxdepth<<<(warps * 32 + 255) / 256, 256, 0, s>>>(depth, H, W, tiles_x, tiles_y, tile_dmax);
-}
-
 void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
                         cudaStream_t s)
 {
-    const int warps = w.tiles_x * w.tiles_y;
-    k_walk_insert<<<(warps * 32 + 127) / 128, 128, 0, s>>>(w, h, tile_dmax, fs, tot);
+    const long long warps = (long long)w.tiles_x * w.tiles_y * w.chunks;
+    k_walk_insert<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(w, h, tile_dmax, fs, tot);
 }
 
 void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,

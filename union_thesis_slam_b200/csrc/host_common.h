@@ -63,6 +63,12 @@ struct FrameIO {
     uint8_t *h_rgb[2] = {nullptr, nullptr};
     double *h_depth[2] = {nullptr, nullptr};
     uint32_t *d_cfold = nullptr;
+    // per-frame scratch: [FrameScratch | tile pyramid levels 1..3] cleared every frame, then level 0
+    uint8_t *d_scratch = nullptr;
+    size_t clear_bytes = 0;
+    FrameScratch *fs = nullptr;
+    TilePyramid pyr{};
+    int tiles_H = 0, tiles_W = 0;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
     cudaEvent_t k_begin = nullptr, k_end = nullptr;
     cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
@@ -76,6 +82,8 @@ struct FrameIO {
     int upload(const uint8_t *rgb, const double *depth, int npix, const uint8_t **d_rgb_out,
                const double **d_depth_out);
     int ensure_cfold(int npix);
+    int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
+    int clear_scratch();              // one memset: FrameScratch + pyramid levels 1..3
     int begin_kernels();
     int end_kernels(); // records timing + releases the upload slot
     int mark(); // records a stage boundary (up to 3 per frame)

@@ -19,6 +19,14 @@ struct FrameScratch {
     int pad;
 };
 
+// Max valid depth per pixel tile, 4 levels: 8, 16, 32, 64 px tiles (0 = no valid pixel in the tile).
+// Level 0 is written by prep_frame, levels 1..3 by atomicMax from the same kernel (they are
+// cleared together with FrameScratch at the start of every frame).
+struct TilePyramid {
+    float *level[4];
+    int tx[4], ty[4];
+};
+
 // Lives for the lifetime of the handle.
 struct Totals {
     unsigned long long updated;      // voxels updated since create
@@ -28,8 +36,8 @@ struct Totals {
 };
 
 void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_t s);
-void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs, int npix,
-                       int sm_count, cudaStream_t s);
+void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
+                       const TilePyramid &pyr, int H, int W, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         BrickRef *list, FrameScratch *fs, cudaStream_t s);
 int integrate_dense_ctas_per_sm();
@@ -65,11 +73,11 @@ struct WalkParams {
     double fx, fy, cx, cy;
     double pose_scale;        // upper bound of the 2-norm of the pose's 3x3 block
     int W, H, tiles_x, tiles_y;
+    int chunks;               // warps per tile: 32 samples each
     int dim_x, dim_y, dim_z;
 };
 
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s);
-void launch_tile_maxdepth(const double *depth, int H, int W, int tiles_x, int tiles_y, float *tile_dmax, cudaStream_t s);
 void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
                         cudaStream_t s);
 void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
