@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    extra = os.environ.get("TSDF_NVCC_EXTRA", "").split()  # e.g. -DINTEGRATE_STAGED=0 for A/B runs
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + sources()
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(os.path.join(HERE, "build.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + res.stdout)

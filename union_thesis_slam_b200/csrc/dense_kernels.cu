@@ -87,8 +87,72 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
 }
 
 // Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
-// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.  The next list entry is
-// fetched while the current brick is processed.
+// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.
+// Records are double-buffered through shared memory: while brick i is integrated, one thread has
+// already started the 6 KB bulk copy (cp.async.bulk + mbarrier, the TMA path) of brick i+1, so the
+// HBM latency of the record is hidden behind a whole brick of float64 geometry.  Updated voxels
+// are written straight from registers with streaming stores.
+#ifndef INTEGRATE_STAGED
+#define INTEGRATE_STAGED 0 // measured: 0.63 vs 0.59 of the HBM roofline on the 1 cm room (profiles/)
+#endif
+#if INTEGRATE_STAGED
+template <bool UNIT_W>
+__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
+k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
+                  FrameScratch *fs, Totals *tot)
+{
+    __shared__ __align__(128) float s_rec[2][BRICK_FLOATS];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int n = fs->vis_count;
+    const int t = threadIdx.x;
+    const int lx = t >> 3, ly = t & 7;
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned my_updates = 0;
+    int b = blockIdx.x;
+    int4 br_next = make_int4(0, 0, 0, 0);
+    if (b < n) {
+        br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
+        if (t == 0) bulk_load_record(s_rec[0], bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS, &s_bar[0]);
+    }
+    uint32_t it = 0;
+    for (; b < n; b += gridDim.x, ++it) {
+        const int4 br = br_next;
+        const uint32_t cur = it & 1u;
+        // everyone is done reading the other buffer (it held brick it-1): refill it with brick it+1
+        __syncthreads();
+        if (b + (int)gridDim.x < n) {
+            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+            if (t == 0)
+                bulk_load_record(s_rec[cur ^ 1u], bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS, &s_bar[cur ^ 1u]);
+        }
+        Staged st;
+        st.smem = s_rec[cur] + 8 * t;
+        st.bar = &s_bar[cur];
+        st.parity = (it >> 1) & 1u;
+        st.waited = false;
+        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
+        if (gx < v.dim_x && gy < v.dim_y)
+            my_updates += integrate_column8<UNIT_W, false, true>(f, v, gx, gy, br.z * BRICK,
+                                                                  bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t, &st);
+        // every thread observes the completion of this phase, so the barrier can be re-armed safely
+        if (!st.waited) mbar_wait(st.bar, st.parity);
+    }
+    for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
+    if ((t & 31) == 0 && my_updates) {
+        atomicAdd(&fs->updated, (unsigned long long)my_updates);
+        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    }
+    if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
+}
+
+#else
+// Variant without shared-memory staging: records are read with streaming loads right after the
+// depth pixels are requested (kept for A/B measurements, -DINTEGRATE_STAGED=0).
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
@@ -103,15 +167,11 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
     for (; b < n; b += gridDim.x) {
         const int4 br = br_next;
-        if (b + (int)gridDim.x < n) {
-            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
-            // pull the next brick's 6 KB record into L2 while this one is integrated
-            if (t == 0) prefetch_record_l2(bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS);
-        }
+        if (b + (int)gridDim.x < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
         my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
-                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
+                                                       bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0 && my_updates) {
@@ -120,6 +180,7 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
     }
     if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
+#endif
 
 // Read-out: bricks -> C-order [n_x][Y][Z] planes (grid_fusion.py:316-320 layout).
 __global__ void k_unbrick(const float *__restrict__ bricks, int n_x, int dim_y, int dim_z, int nby, int nbz,

@@ -3,6 +3,49 @@
 #pragma once
 #include "tsdf_common.cuh"
 
+// ---- record staging through shared memory (TMA-class bulk copy + mbarrier) ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// One elected thread: arm the barrier with the byte count and start the 6 KB bulk copy.
+__device__ __forceinline__ void bulk_load_record(float *dst_smem, const float *src, uint64_t *bar)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(BRICK_FLOATS * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(BRICK_FLOATS * 4), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(b),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Where a quad reads its record from: global memory (rec itself) or a staged copy in shared
+// memory that becomes valid when the mbarrier phase completes.
+struct Staged {
+    const float *smem; // this thread's slot inside the staged record (nullptr: read global)
+    uint64_t *bar;
+    uint32_t parity;
+    bool waited;
+};
+
 // Per-thread body shared by the dense and the hash integrate kernels: geometry of four
 // z-consecutive voxels of one (x, y) column, then read-modify-write of their float4 per plane.
 //   cX/cY/cZ: the column's partial sums fma(T[r][1], wy, T[r][0]*wx); wz[4]: lattice z of the
@@ -15,9 +58,10 @@
 // colour pixels.
 //   PROBE = true: geometry and depth test only -- returns how many voxels WOULD be updated and
 //   never touches rec (used by the hash map to decide whether a block needs storage).
-template <bool UNIT_W, bool PROBE>
+//   FULL = true: all four voxels exist (nvalid is ignored and the masking disappears).
+template <bool UNIT_W, bool PROBE, bool STAGED, bool FULL>
 __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double cX, double cY, double cZ,
-                                                   const double wz[4], int nvalid, float *rec)
+                                                   const double wz[4], int nvalid, float *rec, Staged *st, int h)
 {
     double Z[4], ax[4], ay[4];
     int pix[4];
@@ -25,7 +69,7 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pix[e], cand[e], exact[e]);
-        if (e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
+        if (!FULL && e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
     }
     if (exact[0] || exact[1] || exact[2] || exact[3]) { // ~2^-15 of the voxels
 #pragma unroll
@@ -44,11 +88,23 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     float4 T4 = make_float4(1.f, 1.f, 1.f, 1.f), W4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 C4 = make_uint4(0u, 0u, 0u, 0u);
     if (!PROBE) {
-        T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
-        W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
-        C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
+        if (!STAGED) {
+            T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
+            W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
+            C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) nc[e] = __ldg(f.cfold + pix[e]);
+        if (STAGED) { // the bulk copy was started a whole brick ago; normally this does not block
+            if (!st->waited) {
+                mbar_wait(st->bar, st->parity);
+                st->waited = true;
+            }
+            const float *sr = st->smem + 4 * h;
+            T4 = *reinterpret_cast<const float4 *>(sr);
+            W4 = *reinterpret_cast<const float4 *>(sr + BRICK_VOX);
+            C4 = *reinterpret_cast<const uint4 *>(sr + 2 * BRICK_VOX);
+        }
     }
     double diff[4];
     bool pass[4], band[4];
@@ -63,11 +119,20 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
     uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
     bool slow[4];
+    // non-passing voxels of the quad must not veto the colour shortcut: give them a zero difference
+    uint32_t ncq[4];
+    float wq[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        ncq[e] = pass[e] ? nc[e] : c[e];
+        wq[e] = pass[e] ? w[e] : 1024.0f;
+    }
+    const bool skip_color = UNIT_W && colour_converged4(c, ncq, wq);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         float we = w[e];
         uint32_t ce = c[e];
-        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, band[e], nc[e]);
+        const bool ok = update_voxel_fast<UNIT_W>(f, t[e], we, ce, band[e], nc[e], skip_color);
         if (pass[e] && ok) { w[e] = we; c[e] = ce; }
         slow[e] = pass[e] && !ok;
     }
@@ -90,9 +155,9 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
 }
 
 // One (x, y) column of a brick: 8 voxels as two quads.  Returns the number of voxels updated.
-template <bool UNIT_W, bool PROBE>
+template <bool UNIT_W, bool PROBE, bool STAGED = false>
 __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, const VolumeParams &v, int gx, int gy,
-                                                      int gz0, float *rec)
+                                                      int gz0, float *rec, Staged *st = nullptr)
 {
     const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
     const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
@@ -107,7 +172,10 @@ __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, cons
         const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz));
         const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz) + 1);
         const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
-        n += integrate_quad<UNIT_W, PROBE>(f, cX, cY, cZ, wz, nvalid, rec + 4 * h);
+        if (nvalid >= 4)
+            n += integrate_quad<UNIT_W, PROBE, STAGED, true>(f, cX, cY, cZ, wz, 4, rec + 4 * h, st, h);
+        else
+            n += integrate_quad<UNIT_W, PROBE, STAGED, false>(f, cX, cY, cZ, wz, nvalid, rec + 4 * h, st, h);
     }
     return n;
 }

@@ -52,8 +52,9 @@ def trajectory(n, room, seed=0, margin=0.8):
     return poses
 
 
-def render_room(pose, K, room, width=640, height=480, holes=True):
-    """Returns (color uint8 [H,W,3], depth float64 [H,W] metres)."""
+def render_room(pose, K, room, width=640, height=480, holes=True, noise=0, rng=None):
+    """Returns (color uint8 [H,W,3], depth float64 [H,W] metres).  noise > 0 adds uniform integer
+    sensor noise in [-noise, noise] to every colour channel (seeded by rng)."""
     room = np.asarray(room, float)
     v, u = np.mgrid[0:height, 0:width]
     rays = np.stack([(u - K[0, 2]) / K[0, 0], (v - K[1, 2]) / K[1, 1], np.ones_like(u, float)], -1)
@@ -79,15 +80,19 @@ def render_room(pose, K, room, width=640, height=480, holes=True):
     chk = (cell.sum(-1) + wall) & 1
     base = np.array([[200, 60, 60], [60, 200, 60], [60, 60, 200], [200, 200, 60], [200, 60, 200], [60, 200, 200]])
     color = base[wall] + 40 * chk[..., None] + (cell[..., :3] % 8)
+    if noise:
+        color = color + (rng or np.random.default_rng(0)).integers(-noise, noise + 1, color.shape)
     return np.clip(color, 0, 255).astype(np.uint8), depth
 
 
-def room_stream(n, room, width=640, height=480, seed=0, holes=True):
-    """n frames: list of (color, depth, pose) plus the intrinsics."""
+def room_stream(n, room, width=640, height=480, seed=0, holes=True, noise=4):
+    """n frames: list of (color, depth, pose) plus the intrinsics.  Colours carry +-noise of
+    per-frame sensor noise so that consecutive observations of a voxel never agree exactly."""
     K = intrinsics(width, height)
     frames = []
+    rng = np.random.default_rng(seed + 1000)
     for pose in trajectory(n, room, seed):
-        c, d = render_room(pose, K, room, width, height, holes)
+        c, d = render_room(pose, K, room, width, height, holes, noise, rng)
         frames.append((c, d, pose))
     return frames, K
 
