@@ -12,14 +12,15 @@ vol = grid_fusion.TSDFVolume(room.copy(), vs)
 dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), np.linalg.inv(p)) for c, d, p in frames]
 torch.cuda.synchronize()
 H, W = frames[0][1].shape
-for rep in range(3):
+REPS = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+for rep in range(REPS):
     tot_ms = 0.0; tot_u = 0
     t0 = time.perf_counter()
     for dc, dd, ti in dev:
         vol.integrate_device(dc, dd, H, W, K, ti, 1.0)
         ms = vol.last_kernel_ms(); st = vol.stats()
         tot_ms += ms; tot_u += st["updated_last"]
-        if rep == 2:
+        if rep == REPS - 1:
             by = 24.0 * st["updated_last"] + 12.0 * H * W
             print("frame: %.3f ms  updated %d  bricks %d  -> %.0f GB/s algorithmic (%.1f%% of 6551)" % (
                 ms, st["updated_last"], st["bricks_visited_last"], by / ms / 1e6, by / ms / 1e6 / 65.51))

@@ -63,19 +63,19 @@ template <bool UNIT_W, bool PROBE, bool STAGED, bool FULL>
 __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double cX, double cY, double cZ,
                                                    const double wz[4], int nvalid, float *rec, Staged *st, int h)
 {
-    double Z[4], ax[4], ay[4];
+    double Z[4];
     int pix[4];
     bool cand[4], exact[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        Z[e] = project_fast(f, cX, cY, cZ, wz[e], ax[e], ay[e], pix[e], cand[e], exact[e]);
+        Z[e] = project_fast(f, cX, cY, cZ, wz[e], pix[e], cand[e], exact[e]);
         if (!FULL && e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
     }
     if (exact[0] || exact[1] || exact[2] || exact[3]) { // ~2^-15 of the voxels
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (exact[e]) {
-                const int p = exact_pixel(ax[e], ay[e], Z[e], f.cx, f.cy, f.W, f.H);
+                const int p = exact_pixel(f.T[2], f.T[3], f.T[6], f.T[7], cX, cY, wz[e], Z[e], f.fx, f.fy, f.cx, f.cy, f.W, f.H);
                 if (p >= 0) { pix[e] = p; cand[e] = true; }
             }
     }
