@@ -305,7 +305,7 @@ def bench_hash(args, dev, local, frames, K, room, peak):
         ht.integrate_device(dc, dd, IM_H, IM_W, K, ti, 1.0)
         tot_ms += ht.last_kernel_ms()
         st = ht.stats()
-        tot_bytes += 24.0 * st["updated_last"] + 16.0 * st["candidates_last"] + 12.0 * IM_W * IM_H
+        tot_bytes += 24.0 * st["updated_last"] + 16.0 * (st["blocks_visited_last"] + st["keys_inserted_last"]) + 12.0 * IM_W * IM_H
     wall = time.perf_counter() - t0
     s1 = ht.stats()
     upd = s1["updated_total"] - s0["updated_total"]
@@ -314,7 +314,7 @@ def bench_hash(args, dev, local, frames, K, room, peak):
             "frames_per_s": steps / (tot_ms * 1e-3), "ms_per_step": tot_ms / steps,
             "voxel_size_m": HASH_VOXEL, "blocks": s1["blocks"], "table_slots": s1["table_slots"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "bytes_model": "24 B x voxels updated + 16 B x candidate keys + 12 B x pixels, whole "
+                         "bytes_model": "24 B x voxels updated + 16 B x unique keys (visible + inserted) + 12 B x pixels, whole "
                                         "pipeline (ray walk + insert + compaction + integrate) device time"},
             "wall_s": wall}
 

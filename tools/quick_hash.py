@@ -22,7 +22,7 @@ for rep in range(3):
         ms = ht.last_kernel_ms(); st = ht.stats()
         tot_ms += ms; tot_u += st["updated_last"]
         if rep == 2:
-            by = 24.0 * st["updated_last"] + 16.0 * st["candidates_last"] + 12.0 * H * W
+            by = 24.0 * st["updated_last"] + 16.0 * (st["blocks_visited_last"] + st["keys_inserted_last"]) + 12.0 * H * W
             print("frame: %.3f ms updated %d visited %d cand %d newkeys %d keys %d blocks %d -> %.0f GB/s (%.1f%%)" % (
                 ms, st["updated_last"], st["blocks_visited_last"], st["candidates_last"], st["keys_inserted_last"],
                 st["table_keys"], st["blocks"], by / ms / 1e6, by / ms / 1e6 / 65.51))

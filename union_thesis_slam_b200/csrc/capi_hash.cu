@@ -14,10 +14,12 @@ struct tsdf_hash {
     BrickRef *vis_list = nullptr;
     Totals *tot = nullptr;
     int *scratch_count = nullptr; // device int used by export / remove
+    uint32_t *sb_flags = nullptr; // per-frame bitmap of super-blocks touched by the ray walk
+    size_t sb_words = 0;
     int integrate_grid = 0;
     int64_t frames = 0;
     bool unit_w = true;
-    double walk_step_voxels = 4.0; // ray-walk sample spacing: half a block
+    double walk_step_voxels = 16.0; // ray-walk sample spacing: half a super-block
 };
 
 static int hash_free(tsdf_hash *h)
@@ -27,7 +29,7 @@ static int hash_free(tsdf_hash *h)
     h->io.release();
     h->geom.release();
     void *ptrs[] = {h->dev.keys, h->dev.vals, h->dev.entries, h->dev.n_entries, h->dev.heap, h->dev.heap_top,
-                    h->dev.blocks, h->vis_list, h->tot, h->scratch_count};
+                    h->dev.blocks, h->dev.known, h->vis_list, h->tot, h->scratch_count, h->sb_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -56,9 +58,9 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         return rc;
     }
     for (int a = 0; a < 3; ++a)
-        if (h->geom.nb[a] >= (1 << 21)) {
+        if (h->geom.nb[a] >= (1 << 15)) { // visible-list entries pack bx | by << 16
             hash_free(h);
-            tsdf_set_error("volume has too many blocks along axis %d for 21-bit key fields", a);
+            tsdf_set_error("volume has too many blocks along axis %d (limit 32767)", a);
             return TSDF_ERR_BAD_ARG;
         }
     int64_t S = 1024;
@@ -70,6 +72,10 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
     d.heap_cap = (int)heap_blocks;
     d.rank = rank;
     d.world = world;
+    d.nbx = h->geom.nb[0]; d.nby = h->geom.nb[1]; d.nbz = h->geom.nb[2];
+    d.nsx = (d.nbx + 3) / 4; d.nsy = (d.nby + 3) / 4; d.nsz = (d.nbz + 3) / 4;
+    const size_t known_words = ((size_t)d.nbx * d.nby * d.nbz + 31) / 32;
+    h->sb_words = ((size_t)d.nsx * d.nsy * d.nsz + 31) / 32;
     cudaError_t e;
     if ((e = cudaMalloc(&d.keys, S * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc(&d.vals, S * sizeof(uint32_t))) != cudaSuccess ||
@@ -78,6 +84,8 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         (e = cudaMalloc(&d.heap, heap_blocks * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&d.heap_top, sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&d.known, known_words * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&h->sb_flags, h->sb_words * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&h->vis_list, S * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
         (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
@@ -176,7 +184,9 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     if ((rc = h->io.begin_kernels())) return rc;
     if ((rc = h->io.clear_scratch())) return rc;
     launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->io.fs, h->io.pyr, H, W, s);
-    launch_walk_insert(w, h->dev, h->io.pyr.level[0], h->io.fs, h->tot, s);
+    CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
+    launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
+    launch_refine_insert(f, c, h->dev, h->sb_flags, h->io.fs, h->tot, s);
     launch_compact_visible(f, c, h->dev, (int)h->table_slots, h->vis_list, h->io.fs, s);
     launch_integrate_hash(f, h->geom.params(), h->dev, h->vis_list, h->io.fs, h->tot, h->integrate_grid, s);
     CUDA_TRY(cudaGetLastError());

@@ -11,11 +11,13 @@
 //
 // Per frame
 //   (prep_frame builds the per-tile max-depth pyramid, dense_kernels.cu)
-//   K2/K3 walk_insert   one warp per 8x8-pixel tile walks the tile's cone from the camera to
-//                       (max depth of the tile + trunc) in half-block steps and emits every block
-//                       the dilated sample touches; duplicates are removed inside the warp with
-//                       __match_any_sync, the leaders look the key up and insert it lock-free
-//                       (atomicCAS on the key word).  Keys only -- no storage yet.
+//   K2   walk_coarse    one warp per (8x8-pixel tile, 32 samples) walks the tile's cone from the
+//                       camera to (max depth of the tile + trunc) and flags every 32^3-voxel
+//                       super-block the conservatively dilated samples touch; duplicates inside the
+//                       warp are removed with __match_any_sync before the atomicOr
+//   K3   refine_insert  one warp per flagged super-block: blocks whose key is not yet known are
+//                       tested with the dense grid's conservative visibility test and inserted
+//                       lock-free (atomicCAS on the 64-bit key word).  Keys only -- no storage yet.
 //   K4   compact        frustum/depth-range test of every table entry, warp ballot + prefix sum,
 //                       one atomic per warp -> visible block list
 //   K5   integrate      persistent CTAs, one block per iteration, the dense per-voxel rule.  A key
@@ -95,12 +97,14 @@ __device__ __forceinline__ void table_insert(const HashDev &h, unsigned long lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 + K3: cone walk per pixel tile, warp-aggregated dedup, lock-free insertion.
-__global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__ tile_dmax, FrameScratch *fs,
-                              Totals *tot)
+// K2: cone walk per pixel tile over SUPER-BLOCKS (4x4x4 blocks = 32^3 voxels).  One warp per
+// (tile, chunk of 32 samples); a sample stands for the slice of the tile's cone within half a step
+// of its depth, and every super-block that slice can touch (axis-aligned box of the sample dilated
+// by the along-ray half step and the cone half width, all conservative) is flagged in a per-frame
+// bitmap.  Lanes that hit the same super-block elect one leader (__match_any_sync) for the atomicOr.
+__global__ void k_walk_coarse(WalkParams w, HashDev h, const float *__restrict__ tile_dmax, uint32_t *sb_flags,
+                              FrameScratch *fs)
 {
-    // one warp per (tile, chunk of 32 consecutive samples): many short independent walks instead
-    // of few long ones, so the table probes of different chunks overlap
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int tile = warp / w.chunks, chunk = warp - tile * w.chunks;
@@ -113,21 +117,20 @@ __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__
     // centre ray of the tile and its lateral half-extent per unit depth (+0.51 px: pixel rounding)
     const double dcx = (0.5 * (u0 + u1) - w.cx) / w.fx, dcy = (0.5 * (v0 + v1) - w.cy) / w.fy;
     const double hx = (0.5 * (u1 - u0) + 0.51) / fabs(w.fx), hy = (0.5 * (v1 - v0) + 0.51) / fabs(w.fy);
-    const double lat = sqrt(hx * hx + hy * hy) * w.pose_scale;
+    const double lat = sqrt(hx * hx + hy * hy) * w.pose_scale * w.inv_vs; // cone half width, voxels per metre of depth
     // ray in voxel-index space: g(s) = e + s * d
-    const double dx = (w.P[0] * dcx + w.P[1] * dcy + w.P[2]) * w.inv_vs;
-    const double dy = (w.P[4] * dcx + w.P[5] * dcy + w.P[6]) * w.inv_vs;
-    const double dz = (w.P[8] * dcx + w.P[9] * dcy + w.P[10]) * w.inv_vs;
-    const double ex = (w.P[3] - w.ox) * w.inv_vs, ey = (w.P[7] - w.oy) * w.inv_vs, ez = (w.P[11] - w.oz) * w.inv_vs;
-    const double dlen = sqrt(dx * dx + dy * dy + dz * dz); // voxels of path per metre of depth
+    const double dd[3] = {(w.P[0] * dcx + w.P[1] * dcy + w.P[2]) * w.inv_vs,
+                          (w.P[4] * dcx + w.P[5] * dcy + w.P[6]) * w.inv_vs,
+                          (w.P[8] * dcx + w.P[9] * dcy + w.P[10]) * w.inv_vs};
+    const double ee[3] = {(w.P[3] - w.ox) * w.inv_vs, (w.P[7] - w.oy) * w.inv_vs, (w.P[11] - w.oz) * w.inv_vs};
+    const double hi[3] = {(double)w.dim_x, (double)w.dim_y, (double)w.dim_z};
     const double s_end = (double)dmax + w.trunc;
-    // clip [0, s_end] to the slab where the cone can touch the volume (index box dilated by the cone radius)
-    const double rmax = 0.5 * w.step * dlen + lat * w.inv_vs * (s_end + w.step) + 1.0;
+    // clip [0, s_end] to where the cone can touch the volume (index box dilated by the largest radius)
     double s0 = 0.0, s1 = s_end;
-    const double dd[3] = {dx, dy, dz}, ee[3] = {ex, ey, ez}, hi[3] = {(double)w.dim_x, (double)w.dim_y, (double)w.dim_z};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const double lo_b = -rmax - 1.0, hi_b = hi[a] + rmax;
+        const double rmax = 0.5 * w.step * fabs(dd[a]) + lat * (s_end + w.step) + 2.0;
+        const double lo_b = -rmax, hi_b = hi[a] + rmax;
         if (fabs(dd[a]) < 1e-12) {
             if (ee[a] < lo_b || ee[a] > hi_b) return;
         } else {
@@ -144,32 +147,59 @@ __global__ void k_walk_insert(WalkParams w, HashDev h, const float *__restrict__
     const int j_end = (chunk == w.chunks - 1) ? nsamp : min(nsamp, (chunk + 1) * 32);
     for (int j = chunk * 32 + lane; j < j_end; j += 32) {
         const double s = fmin(s0 + j * w.step, s_end);
-        // every voxel centre a pixel of this tile can update at depth in [s - step/2, s + step/2]
-        // lies within rr voxels of the sample (along-ray half step + cone half width + slack)
-        const double rr = (0.5 * w.step * dlen + lat * w.inv_vs * (s + 0.5 * w.step)) * 1.001 + 0.02;
-        const double gx = ex + s * dx, gy = ey + s * dy, gz = ez + s * dz;
-        int ilo[3], ihi[3];
-        ilo[0] = max((int)ceil(gx - rr), 0); ihi[0] = min((int)floor(gx + rr), w.dim_x - 1);
-        ilo[1] = max((int)ceil(gy - rr), 0); ihi[1] = min((int)floor(gy + rr), w.dim_y - 1);
-        ilo[2] = max((int)ceil(gz - rr), 0); ihi[2] = min((int)floor(gz + rr), w.dim_z - 1);
-        if (ilo[0] > ihi[0] || ilo[1] > ihi[1] || ilo[2] > ihi[2]) continue;
-        for (int bx = ilo[0] >> 3; bx <= (ihi[0] >> 3); ++bx)
-            for (int by = ilo[1] >> 3; by <= (ihi[1] >> 3); ++by)
-                for (int bz = ilo[2] >> 3; bz <= (ihi[2] >> 3); ++bz) {
-                    const unsigned long long key = pack_key(bx, by, bz);
-                    // warp-aggregated dedup: lanes that emit the same key elect one leader
-                    const unsigned active = __activemask();
-                    const unsigned peers = __match_any_sync(active, key);
-                    if (lane != __ffs(peers) - 1) continue;
-                    if (h.world > 1 && owner_of(key, h.world) != h.rank) continue;
+        // every voxel centre a pixel of this tile can update at depth in [s - step/2, s + step/2] lies,
+        // per axis, within (half step along the ray + cone half width) of the sample
+        const double rl = lat * (s + 0.5 * w.step) * 1.001 + 0.02;
+        int lo[3], hi_i[3];
+        bool empty = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double g = ee[a] + s * dd[a], r = 0.5 * w.step * fabs(dd[a]) * 1.001 + rl;
+            lo[a] = max((int)ceil(g - r), 0);
+            hi_i[a] = min((int)floor(g + r), (int)hi[a] - 1);
+            empty = empty || lo[a] > hi_i[a];
+        }
+        if (empty) continue;
+        for (int sx = lo[0] >> 5; sx <= (hi_i[0] >> 5); ++sx)
+            for (int sy = lo[1] >> 5; sy <= (hi_i[1] >> 5); ++sy)
+                for (int sz = lo[2] >> 5; sz <= (hi_i[2] >> 5); ++sz) {
                     ++my_cand;
-                    table_insert(h, key, bx, by, bz, fs, tot);
+                    const uint32_t bit = (uint32_t)((sx * h.nsy + sy) * h.nsz + sz);
+                    if ((sb_flags[bit >> 5] >> (bit & 31u)) & 1u) continue; // already flagged this frame
+                    const unsigned peers = __match_any_sync(__activemask(), bit);
+                    if (lane == __ffs(peers) - 1) atomicOr(sb_flags + (bit >> 5), 1u << (bit & 31u));
                 }
     }
-    // one counter update per warp (a per-candidate atomic on one address serialises the kernel)
     __syncwarp();
     for (int o = 16; o; o >>= 1) my_cand += __shfl_xor_sync(0xffffffffu, my_cand, o);
     if (lane == 0 && my_cand) atomicAdd(&fs->cand_count, my_cand);
+}
+
+// K3: one warp per flagged super-block; each lane tests two of its 64 blocks.  A block whose key
+// is already in the table (presence bitmap) costs one bit test; otherwise the conservative
+// visibility test of the dense grid decides and the key is inserted lock-free (keys only).
+__global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, const uint32_t *__restrict__ sb_flags,
+                                FrameScratch *fs, Totals *tot)
+{
+    const int sb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (sb >= h.nsx * h.nsy * h.nsz) return;
+    if (!((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
+    const int sz = sb % h.nsz, sy = (sb / h.nsz) % h.nsy, sx = sb / (h.nsz * h.nsy);
+    c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+    if (!(c.max_depth > 0.0)) return;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int child = lane * 2 + k;
+        const int bx = sx * 4 + (child >> 4), by = sy * 4 + ((child >> 2) & 3), bz = sz * 4 + (child & 3);
+        if (bx >= h.nbx || by >= h.nby || bz >= h.nbz) continue;
+        const uint32_t bit = (uint32_t)((bx * h.nby + by) * h.nbz + bz);
+        if ((h.known[bit >> 5] >> (bit & 31u)) & 1u) continue;
+        if (!brick_visible(f, c, bx, by, bz)) continue;
+        const unsigned long long key = pack_key(bx, by, bz);
+        if (h.world == 1 || owner_of(key, h.world) == h.rank) table_insert(h, key, bx, by, bz, fs, tot);
+        atomicOr(h.known + (bit >> 5), 1u << (bit & 31u)); // ours and inserted, or not ours: never test again
+    }
 }
 
 // K4: visible-block compaction over the entry list.
@@ -194,8 +224,9 @@ __global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickR
     if (lane == 0) base = atomicAdd(&fs->vis_count, __popc(ballot));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (vis) {
+        // list entry of the hash map: (bx | by << 16, bz, table slot, record index or NONE)
         BrickRef r;
-        r.bx = bx; r.by = by; r.bz = bz; r.storage = slot;
+        r.bx = bx | (by << 16); r.by = bz; r.bz = (int)slot; r.storage = h.vals[slot];
         list[base + __popc(ballot & ((1u << lane) - 1u))] = r;
     }
 }
@@ -210,11 +241,15 @@ k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__res
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
     unsigned my_updates = 0;
-    for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int4 br = __ldg(reinterpret_cast<const int4 *>(list) + b);
-        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly, gz0 = br.z * BRICK;
+    int b = blockIdx.x;
+    int4 br_next = make_int4(0, 0, 0, 0);
+    if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
+    for (; b < n; b += gridDim.x) {
+        const int4 br = br_next; // (bx | by << 16, bz, slot, storage)
+        if (b + (int)gridDim.x < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+        const int gx = (br.x & 0xFFFF) * BRICK + lx, gy = (br.x >> 16) * BRICK + ly, gz0 = br.y * BRICK;
         const bool inb = gx < v.dim_x && gy < v.dim_y;
-        uint32_t storage = h.vals[(uint32_t)br.w]; // CTA-uniform
+        uint32_t storage = (uint32_t)br.w; // CTA-uniform
         if (storage == VAL_NONE) {
             // key without storage: geometry-only probe, allocate iff some voxel will be updated
             const unsigned would = inb ? integrate_column8<UNIT_W, true>(f, v, gx, gy, gz0, nullptr) : 0u;
@@ -224,7 +259,7 @@ k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__res
                 uint32_t blk = VAL_NONE;
                 if (top >= 0) {
                     blk = h.heap[top];
-                    h.vals[(uint32_t)br.w] = blk;
+                    h.vals[(uint32_t)br.z] = blk;
                 } else {
                     atomicAdd(h.heap_top, 1);
                     raise_error(tot, TSDF_ERR_HEAP_EXHAUSTED_CODE);
@@ -267,6 +302,8 @@ __global__ void k_hash_init(HashDev h)
         h.vals[i] = VAL_NONE;
     }
     for (size_t i = i0; i < (size_t)h.heap_cap; i += stride) h.heap[i] = (uint32_t)(h.heap_cap - 1 - i);
+    const size_t nwords = ((size_t)h.nbx * h.nby * h.nbz + 31) / 32;
+    for (size_t i = i0; i < nwords; i += stride) h.known[i] = 0u;
     if (i0 == 0) {
         *h.n_entries = 0;
         *h.heap_top = h.heap_cap;
@@ -351,11 +388,18 @@ __global__ void k_remove_blocks(HashDev h, const int32_t *keys, int n, int *remo
 // ---------------------------------------------------------------------------------------------
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s) { k_hash_init<<<sm_count * 4, 256, 0, s>>>(h); }
 
-void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
-                        cudaStream_t s)
+void launch_walk_coarse(const WalkParams &w, const HashDev &h, const float *tile_dmax, uint32_t *sb_flags,
+                        FrameScratch *fs, cudaStream_t s)
 {
     const long long warps = (long long)w.tiles_x * w.tiles_y * w.chunks;
-    k_walk_insert<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(w, h, tile_dmax, fs, tot);
+    k_walk_coarse<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(w, h, tile_dmax, sb_flags, fs);
+}
+
+void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+                          FrameScratch *fs, Totals *tot, cudaStream_t s)
+{
+    const long long warps = (long long)h.nsx * h.nsy * h.nsz;
+    k_refine_insert<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(f, c, h, sb_flags, fs, tot);
 }
 
 void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
