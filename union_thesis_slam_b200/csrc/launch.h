@@ -60,6 +60,9 @@ struct HashDev {
     int *heap_top;            // number of free records
     int heap_cap;
     float *blocks;            // [heap_cap][1536]
+    uint32_t *known;          // bitmap over the bounded block grid: key already in the table
+    int nbx, nby, nbz;        // block grid of the volume
+    int nsx, nsy, nsz;        // super-block grid (4x4x4 blocks)
     int rank, world;
 };
 
@@ -78,8 +81,10 @@ struct WalkParams {
 };
 
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s);
-void launch_walk_insert(const WalkParams &w, const HashDev &h, const float *tile_dmax, FrameScratch *fs, Totals *tot,
-                        cudaStream_t s);
+void launch_walk_coarse(const WalkParams &w, const HashDev &h, const float *tile_dmax, uint32_t *sb_flags,
+                        FrameScratch *fs, cudaStream_t s);
+void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+                          FrameScratch *fs, Totals *tot, cudaStream_t s);
 void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
                             BrickRef *list, FrameScratch *fs, cudaStream_t s);
 int integrate_hash_ctas_per_sm();
