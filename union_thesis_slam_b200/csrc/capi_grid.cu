@@ -135,9 +135,12 @@ int FrameIO::init()
 {
     CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&pre, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pre_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&int_done[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreate(&k_begin));
     CUDA_TRY(cudaEventCreate(&k_end));
@@ -147,13 +150,14 @@ int FrameIO::init()
 
 int FrameIO::ensure_cfold(int npix)
 {
-    if (npix <= cap_pix && d_cfold) return TSDF_OK;
+    if (npix <= cap_pix && cfold_slot[0]) return TSDF_OK;
     return ensure(npix);
 }
 
 int FrameIO::ensure(int npix)
 {
     if (npix <= cap_pix) return TSDF_OK;
+    CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
     CUDA_TRY(cudaStreamSynchronize(copy));
     for (int i = 0; i < 2; ++i) {
@@ -161,9 +165,9 @@ int FrameIO::ensure(int npix)
         if (d_depth[i]) cudaFree(d_depth[i]);
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
         if (h_depth[i]) cudaFreeHost(h_depth[i]);
-        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr;
+        if (cfold_slot[i]) cudaFree(cfold_slot[i]);
+        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr; cfold_slot[i] = nullptr;
     }
-    if (d_cfold) cudaFree(d_cfold);
     d_cfold = nullptr;
     cap_pix = 0;
     for (int i = 0; i < 2; ++i) {
@@ -171,42 +175,41 @@ int FrameIO::ensure(int npix)
         CUDA_TRY(cudaMalloc(&d_depth[i], (size_t)npix * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMallocHost(&h_depth[i], (size_t)npix * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&cfold_slot[i], (size_t)npix * sizeof(uint32_t)));
     }
-    CUDA_TRY(cudaMalloc(&d_cfold, (size_t)npix * sizeof(uint32_t)));
     cap_pix = npix;
     return TSDF_OK;
 }
 
 int FrameIO::ensure_tiles(int H, int W)
 {
-    if (d_scratch && H == tiles_H && W == tiles_W) return TSDF_OK;
+    if (scratch_slot[0] && H == tiles_H && W == tiles_W) return TSDF_OK;
+    CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
-    if (d_scratch) cudaFree(d_scratch);
-    d_scratch = nullptr;
     size_t off[4], total = 256; // FrameScratch lives in the first 256 bytes
+    TilePyramid p{};
     for (int l = 1; l <= 3; ++l) {
-        pyr.tx[l] = (W + (8 << l) - 1) / (8 << l);
-        pyr.ty[l] = (H + (8 << l) - 1) / (8 << l);
+        p.tx[l] = (W + (8 << l) - 1) / (8 << l);
+        p.ty[l] = (H + (8 << l) - 1) / (8 << l);
         off[l] = total;
-        total += (((size_t)pyr.tx[l] * pyr.ty[l] * sizeof(float)) + 255) / 256 * 256;
+        total += (((size_t)p.tx[l] * p.ty[l] * sizeof(float)) + 255) / 256 * 256;
     }
     clear_bytes = total;
-    pyr.tx[0] = (W + 7) / 8;
-    pyr.ty[0] = (H + 7) / 8;
+    p.tx[0] = (W + 7) / 8;
+    p.ty[0] = (H + 7) / 8;
     off[0] = total;
-    total += (size_t)pyr.tx[0] * pyr.ty[0] * sizeof(float);
-    CUDA_TRY(cudaMalloc(&d_scratch, total));
-    CUDA_TRY(cudaMemsetAsync(d_scratch, 0, total, compute));
-    fs = reinterpret_cast<FrameScratch *>(d_scratch);
-    for (int l = 0; l < 4; ++l) pyr.level[l] = reinterpret_cast<float *>(d_scratch + off[l]);
+    total += (size_t)p.tx[0] * p.ty[0] * sizeof(float);
+    for (int i = 0; i < 2; ++i) {
+        if (scratch_slot[i]) cudaFree(scratch_slot[i]);
+        scratch_slot[i] = nullptr;
+        CUDA_TRY(cudaMalloc(&scratch_slot[i], total));
+        CUDA_TRY(cudaMemset(scratch_slot[i], 0, total));
+        pyr_slot[i] = p;
+        for (int l = 0; l < 4; ++l) pyr_slot[i].level[l] = reinterpret_cast<float *>(scratch_slot[i] + off[l]);
+    }
+    fs = nullptr;
     tiles_H = H;
     tiles_W = W;
-    return TSDF_OK;
-}
-
-int FrameIO::clear_scratch()
-{
-    CUDA_TRY(cudaMemsetAsync(d_scratch, 0, clear_bytes, compute));
     return TSDF_OK;
 }
 
@@ -243,7 +246,7 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     CUDA_TRY(cudaMemcpyAsync(d_depth[s], src_depth, (size_t)npix * sizeof(double), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
-    CUDA_TRY(cudaStreamWaitEvent(compute, h2d_done[s], 0));
+    CUDA_TRY(cudaStreamWaitEvent(pre, h2d_done[s], 0));
     // the caller's buffers are only borrowed for the duration of the call
     if (pinned) CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
     cur = s;
@@ -254,8 +257,22 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
 
 int FrameIO::begin_kernels()
 {
-    CUDA_TRY(cudaEventRecord(k_begin, compute));
+    slot ^= 1;
+    d_cfold = cfold_slot[slot];
+    fs = reinterpret_cast<FrameScratch *>(scratch_slot[slot]);
+    pyr = pyr_slot[slot];
+    // the integrate kernel of the frame two calls ago was the last reader of this slot
+    CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
+    CUDA_TRY(cudaEventRecord(k_begin, pre));
+    CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
+    return TSDF_OK;
+}
+
+int FrameIO::prepared()
+{
+    CUDA_TRY(cudaEventRecord(pre_done[slot], pre));
+    CUDA_TRY(cudaStreamWaitEvent(compute, pre_done[slot], 0));
     return TSDF_OK;
 }
 
@@ -283,6 +300,7 @@ int FrameIO::last_stage_ms(float ms[4], int *n)
 int FrameIO::end_kernels()
 {
     CUDA_TRY(cudaEventRecord(k_end, compute));
+    CUDA_TRY(cudaEventRecord(int_done[slot], compute));
     timed = true;
     if (cur >= 0) {
         CUDA_TRY(cudaEventRecord(slot_free[cur], compute));
@@ -302,9 +320,14 @@ int FrameIO::last_ms(float *ms)
 
 void FrameIO::release()
 {
+    if (pre) cudaStreamSynchronize(pre);
     if (compute) cudaStreamSynchronize(compute);
     if (copy) cudaStreamSynchronize(copy);
     for (int i = 0; i < 2; ++i) {
+        if (cfold_slot[i]) cudaFree(cfold_slot[i]);
+        if (scratch_slot[i]) cudaFree(scratch_slot[i]);
+        if (pre_done[i]) cudaEventDestroy(pre_done[i]);
+        if (int_done[i]) cudaEventDestroy(int_done[i]);
         if (d_rgb[i]) cudaFree(d_rgb[i]);
         if (d_depth[i]) cudaFree(d_depth[i]);
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
@@ -312,13 +335,13 @@ void FrameIO::release()
         if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
         if (slot_free[i]) cudaEventDestroy(slot_free[i]);
     }
-    if (d_cfold) cudaFree(d_cfold);
     for (int i = 0; i < 3; ++i)
         if (k_mark[i]) cudaEventDestroy(k_mark[i]);
     if (k_begin) cudaEventDestroy(k_begin);
     if (k_end) cudaEventDestroy(k_end);
     if (compute) cudaStreamDestroy(compute);
     if (copy) cudaStreamDestroy(copy);
+    if (pre) cudaStreamDestroy(pre);
 }
 
 int tsdf_select_device(int device, int *sm_count)
@@ -350,7 +373,7 @@ struct tsdf_grid {
     int64_t n_x_local = 0;     // local voxel rows
     size_t nbricks = 0;
     float *bricks = nullptr;
-    BrickRef *vis_list = nullptr;
+    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
@@ -365,7 +388,8 @@ static int grid_free(tsdf_grid *g)
     g->io.release();
     g->geom.release();
     if (g->bricks) cudaFree(g->bricks);
-    if (g->vis_list) cudaFree(g->vis_list);
+    for (int i = 0; i < 2; ++i)
+        if (g->vis_list[i]) cudaFree(g->vis_list[i]);
     if (g->tot) cudaFree(g->tot);
     delete g;
     return TSDF_OK;
@@ -406,7 +430,8 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     cudaError_t e;
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
     if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list, nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list[0], nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list[1], nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
         cudaGetLastError();
@@ -433,18 +458,20 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
 {
     int rc = g->io.ensure_cfold(H * W);
     if (rc || (rc = g->io.ensure_tiles(H, W))) return rc;
-    cudaStream_t s = g->io.compute;
+    if ((rc = g->io.begin_kernels())) return rc;
+    BrickRef *list = g->vis_list[g->io.slot];
     c.pyr = g->io.pyr;
     f.depth = d_depth;
     f.cfold = g->io.d_cfold;
     g->unit_w = g->unit_w && f.obs == 1.0;
     f.unit_w = g->unit_w ? 1 : 0;
-    if ((rc = g->io.begin_kernels())) return rc;
-    if ((rc = g->io.clear_scratch())) return rc;
-    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, s);
-    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->vis_list, g->io.fs, s);
+    // preparation (stream `pre`, overlaps the previous frame's integrate kernel)
+    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, g->io.pre);
+    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, list, g->io.fs, g->io.pre);
+    if ((rc = g->io.prepared())) return rc;
+    // integration (stream `compute`)
     if (g->profile_stages && (rc = g->io.mark())) return rc;
-    launch_integrate_dense(f, g->geom.params(), g->vis_list, g->bricks, g->io.fs, g->tot, g->integrate_grid, s);
+    launch_integrate_dense(f, g->geom.params(), list, g->bricks, g->io.fs, g->tot, g->integrate_grid, g->io.compute);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
     g->frames++;
@@ -552,6 +579,7 @@ extern "C" int tsdf_grid_sync(tsdf_grid *g)
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
     CUDA_TRY(cudaStreamSynchronize(g->io.copy));
+    CUDA_TRY(cudaStreamSynchronize(g->io.pre));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));
     return TSDF_OK;
 }

@@ -11,7 +11,7 @@ struct tsdf_hash {
     FrameIO io;
     HashDev dev{};
     int64_t table_slots = 0, heap_blocks = 0;
-    BrickRef *vis_list = nullptr;
+    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity
     Totals *tot = nullptr;
     int *scratch_count = nullptr; // device int used by export / remove
     uint32_t *sb_flags = nullptr; // per-frame bitmap of super-blocks touched by the ray walk
@@ -29,7 +29,7 @@ static int hash_free(tsdf_hash *h)
     h->io.release();
     h->geom.release();
     void *ptrs[] = {h->dev.keys, h->dev.vals, h->dev.entries, h->dev.n_entries, h->dev.heap, h->dev.heap_top,
-                    h->dev.blocks, h->dev.known, h->vis_list, h->tot, h->scratch_count, h->sb_flags};
+                    h->dev.blocks, h->dev.known, h->vis_list[0], h->vis_list[1], h->tot, h->scratch_count, h->sb_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -86,7 +86,8 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&d.known, known_words * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&h->sb_flags, h->sb_words * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list, S * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list[0], S * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list[1], S * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
         (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
         tsdf_set_error("device allocation failed (%lld slots, %lld blocks = %.2f GB): %s", (long long)S,
@@ -147,9 +148,7 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
 {
     int rc = h->io.ensure_cfold(H * W);
     if (rc || (rc = h->io.ensure_tiles(H, W))) return rc;
-    cudaStream_t s = h->io.compute;
-    c.pyr = h->io.pyr;
-    const int tiles_x = h->io.pyr.tx[0], tiles_y = h->io.pyr.ty[0];
+    const int tiles_x = h->io.pyr_slot[0].tx[0], tiles_y = h->io.pyr_slot[0].ty[0];
     WalkParams w;
     BAD_ARG(invert_affine(Tinv, w.P) != 0, "Tinv is singular");
     w.ox = (double)h->geom.origin[0]; w.oy = (double)h->geom.origin[1]; w.oz = (double)h->geom.origin[2];
@@ -177,18 +176,27 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     }
     w.dim_x = (int)h->geom.dim[0]; w.dim_y = (int)h->geom.dim[1]; w.dim_z = (int)h->geom.dim[2];
 
+    if ((rc = h->io.begin_kernels())) return rc;
+    BrickRef *list = h->vis_list[h->io.slot];
+    c.pyr = h->io.pyr;
     f.depth = d_depth;
     f.cfold = h->io.d_cfold;
     h->unit_w = h->unit_w && f.obs == 1.0;
     f.unit_w = h->unit_w ? 1 : 0;
-    if ((rc = h->io.begin_kernels())) return rc;
-    if ((rc = h->io.clear_scratch())) return rc;
+    // allocation + compaction (stream `pre`; they only insert keys and read table state, so they
+    // overlap the previous frame's integrate kernel, which only touches records / vals / the heap)
+    cudaStream_t s = h->io.pre;
     launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->io.fs, h->io.pyr, H, W, s);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
     launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
+    CUDA_TRY(cudaGetLastError());
     launch_refine_insert(f, c, h->dev, h->sb_flags, h->io.fs, h->tot, s);
-    launch_compact_visible(f, c, h->dev, (int)h->table_slots, h->vis_list, h->io.fs, s);
-    launch_integrate_hash(f, h->geom.params(), h->dev, h->vis_list, h->io.fs, h->tot, h->integrate_grid, s);
+    CUDA_TRY(cudaGetLastError());
+    launch_compact_visible(f, c, h->dev, (int)h->table_slots, list, h->io.fs, s);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = h->io.prepared())) return rc;
+    launch_integrate_hash(f, h->geom.params(), h->dev, list, h->io.fs, h->tot, h->integrate_grid, h->io.compute);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.end_kernels())) return rc;
     h->frames++;
@@ -264,6 +272,7 @@ extern "C" int vh_sync(tsdf_hash *h)
     BAD_ARG(!h, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->io.copy));
+    CUDA_TRY(cudaStreamSynchronize(h->io.pre));
     CUDA_TRY(cudaStreamSynchronize(h->io.compute));
     return check_device_error(h);
 }

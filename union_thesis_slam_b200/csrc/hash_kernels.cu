@@ -250,6 +250,9 @@ k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__res
         const int gx = (br.x & 0xFFFF) * BRICK + lx, gy = (br.x >> 16) * BRICK + ly, gz0 = br.y * BRICK;
         const bool inb = gx < v.dim_x && gy < v.dim_y;
         uint32_t storage = (uint32_t)br.w; // CTA-uniform
+        // compaction of this frame may have run while the previous frame's integrate kernel was
+        // still allocating records: vals[] is authoritative for entries listed without storage
+        if (storage == VAL_NONE) storage = h.vals[(uint32_t)br.z];
         if (storage == VAL_NONE) {
             // key without storage: geometry-only probe, allocate iff some voxel will be updated
             const unsigned would = inb ? integrate_column8<UNIT_W, true>(f, v, gx, gy, gz0, nullptr) : 0u;

@@ -52,24 +52,34 @@ int tsdf_select_device(int device, int *sm_count);
 int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
                       const double Tinv[16], double obs);
 
-// Double-buffered frame upload.  Host frames go through pinned staging (or straight from the
-// caller's buffer when that is already pinned) on a copy stream; kernels of frame n overlap the
-// upload of frame n+1.
+// Frame plumbing of one handle.
+//  * Host frames go through pinned staging (or straight from the caller's buffer when that is
+//    already pinned) on the `copy` stream.
+//  * Per-frame preparation kernels (colour fold, tile pyramid, culling / ray walk, compaction) run
+//    on the `pre` stream, the integrate kernel on `compute`.  All per-frame scratch (folded colour,
+//    FrameScratch, tile pyramid, and the handles' visible lists) is double-buffered by frame
+//    parity, so the preparation of frame n+1 overlaps the integration of frame n.
 struct FrameIO {
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, pre = nullptr;
     int cap_pix = 0;
     uint8_t *d_rgb[2] = {nullptr, nullptr};
     double *d_depth[2] = {nullptr, nullptr};
     uint8_t *h_rgb[2] = {nullptr, nullptr};
     double *h_depth[2] = {nullptr, nullptr};
-    uint32_t *d_cfold = nullptr;
-    // per-frame scratch: [FrameScratch | tile pyramid levels 1..3] cleared every frame, then level 0
-    uint8_t *d_scratch = nullptr;
+    // per-frame scratch, one set per frame parity: [FrameScratch | tile pyramid levels 1..3]
+    // (cleared every frame), then pyramid level 0
+    uint32_t *cfold_slot[2] = {nullptr, nullptr};
+    uint8_t *scratch_slot[2] = {nullptr, nullptr};
+    TilePyramid pyr_slot[2] = {};
     size_t clear_bytes = 0;
+    int slot = 1; // parity of the frame being issued (toggled by begin_kernels)
+    // views of the current slot (after a frame: of the last frame issued)
+    uint32_t *d_cfold = nullptr;
     FrameScratch *fs = nullptr;
     TilePyramid pyr{};
     int tiles_H = 0, tiles_W = 0;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
+    cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr};
     cudaEvent_t k_begin = nullptr, k_end = nullptr;
     cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
     int n_marks = 0;
@@ -78,14 +88,16 @@ struct FrameIO {
 
     int init();
     int ensure(int npix);
-    // stages the frame and makes `compute` wait for it; returns device pointers of the slot
+    // stages the frame and makes `pre` wait for it; returns device pointers of the slot
     int upload(const uint8_t *rgb, const double *depth, int npix, const uint8_t **d_rgb_out,
                const double **d_depth_out);
     int ensure_cfold(int npix);
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
-    int clear_scratch();              // one memset: FrameScratch + pyramid levels 1..3
+    // picks the frame's scratch slot, waits (on `pre`) until the frame two calls ago has left it,
+    // clears FrameScratch + pyramid levels 1..3
     int begin_kernels();
-    int end_kernels(); // records timing + releases the upload slot
+    int prepared();    // preparation kernels issued: `compute` waits for them
+    int end_kernels(); // integrate issued: records timing, frees the scratch and upload slots
     int mark(); // records a stage boundary (up to 3 per frame)
     int last_ms(float *ms);
     int last_stage_ms(float ms[4], int *n); // durations of the stages delimited by mark()
