@@ -135,7 +135,11 @@ int FrameIO::init()
 {
     CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&pre, cudaStreamNonBlocking));
+    {   // preparation kernels are short and on the critical path of the next frame: highest priority
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&pre, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
@@ -440,7 +444,9 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     }
     cudaMemsetAsync(g->tot, 0, sizeof(Totals), g->io.compute);
     launch_fill_bricks(g->bricks, g->nbricks, sm, g->io.compute);
-    g->integrate_grid = sm * integrate_dense_ctas_per_sm();
+    // the persistent integrate grid leaves INTEGRATE_RESERVE_CTAS CTA slots per SM free so that the
+    // next frame's preparation kernels (other stream) can run beside it
+    g->integrate_grid = sm * std::max(1, integrate_dense_ctas_per_sm() - integrate_reserve_ctas());
     e = cudaStreamSynchronize(g->io.compute);
     if (e != cudaSuccess) {
         tsdf_set_error("grid initialisation failed: %s", cudaGetErrorString(e));

@@ -98,7 +98,7 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
     }
     cudaMemsetAsync(h->tot, 0, sizeof(Totals), h->io.compute);
     launch_hash_init(d, sm, h->io.compute);
-    h->integrate_grid = sm * integrate_hash_ctas_per_sm();
+    h->integrate_grid = sm * std::max(1, integrate_hash_ctas_per_sm() - integrate_reserve_ctas());
     e = cudaStreamSynchronize(h->io.compute);
     if (e != cudaSuccess) {
         tsdf_set_error("hash map initialisation failed: %s", cudaGetErrorString(e));

@@ -92,6 +92,9 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
 // already started the 6 KB bulk copy (cp.async.bulk + mbarrier, the TMA path) of brick i+1, so the
 // HBM latency of the record is hidden behind a whole brick of float64 geometry.  Updated voxels
 // are written straight from registers with streaming stores.
+#ifndef INTEGRATE_L2_PREFETCH
+#define INTEGRATE_L2_PREFETCH 0
+#endif
 #ifndef INTEGRATE_STAGED
 #define INTEGRATE_STAGED 0 // measured: 0.63 vs 0.59 of the HBM roofline on the 1 cm room (profiles/)
 #endif
@@ -167,7 +170,13 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
     for (; b < n; b += gridDim.x) {
         const int4 br = br_next;
-        if (b + (int)gridDim.x < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+        if (b + (int)gridDim.x < n) {
+            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
+#if INTEGRATE_L2_PREFETCH
+            // one bulk-prefetch instruction pulls the next brick's 6 KB record into L2
+            if (t == 0) prefetch_record_l2(bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS);
+#endif
+        }
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
         my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
@@ -221,8 +230,13 @@ void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int
 {
     const long long n = (long long)nlbx * nby * nbz;
     if (!n) return;
-    k_cull_bricks<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, list, fs);
+    k_cull_bricks<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, list, fs);
 }
+
+#ifndef INTEGRATE_RESERVE_CTAS
+#define INTEGRATE_RESERVE_CTAS 2
+#endif
+int integrate_reserve_ctas() { return INTEGRATE_RESERVE_CTAS; }
 
 int integrate_dense_ctas_per_sm()
 {

@@ -409,7 +409,7 @@ void launch_compact_visible(const FrameParams &f, const CullParams &c, const Has
                             BrickRef *list, FrameScratch *fs, cudaStream_t s)
 {
     if (max_entries <= 0) return;
-    k_compact_visible<<<(max_entries + 255) / 256, 256, 0, s>>>(f, c, h, list, fs);
+    k_compact_visible<<<(max_entries + 127) / 128, 128, 0, s>>>(f, c, h, list, fs);
 }
 
 int integrate_hash_ctas_per_sm()

@@ -41,6 +41,7 @@ void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold,
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         BrickRef *list, FrameScratch *fs, cudaStream_t s);
 int integrate_dense_ctas_per_sm();
+int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
                             FrameScratch *fs, Totals *tot, int grid, cudaStream_t s);
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
