@@ -236,7 +236,12 @@ def run_b200(args):
     traffic_file = os.path.join(ROOT, "profiles", "dense_traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
-            roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+            tj = json.load(fh)
+        # ncu dram__bytes_read+write of one captured launch, scaled to this run's mean launch by the
+        # measured traffic/algorithmic ratio (launches differ only in how many bricks they touch)
+        roofline["traffic"] = tj["ratio_traffic_over_algorithmic"] * roofline["algorithmic_bytes_per_launch"]
+        roofline["traffic_source"] = "profiles/dense_traffic.json: %.2f x algorithmic bytes (ncu, %s)" % (
+            tj["ratio_traffic_over_algorithmic"], tj["kernel"])
 
     # ---- end to end through the drop-in API: pinned host frames in, counters out, every step --
     h_frames = []

@@ -193,7 +193,9 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     CUDA_TRY(cudaGetLastError());
     launch_refine_insert(f, c, h->dev, h->sb_flags, h->io.fs, h->tot, s);
     CUDA_TRY(cudaGetLastError());
-    launch_compact_visible(f, c, h->dev, (int)h->table_slots, list, h->io.fs, s);
+    // a key exists at most once per block of the bounded grid: bound the scan by that, not by the table size
+    launch_compact_visible(f, c, h->dev, (int)std::min<int64_t>(h->table_slots, (int64_t)h->dev.nbx * h->dev.nby * h->dev.nbz),
+                           list, h->io.fs, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.prepared())) return rc;
     launch_integrate_hash(f, h->geom.params(), h->dev, list, h->io.fs, h->tot, h->integrate_grid, h->io.compute);
