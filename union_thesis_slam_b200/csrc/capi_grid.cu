@@ -109,6 +109,12 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     f->cy = (double)(float)K[5];
     BAD_ARG(!isfinite(f->fx) || !isfinite(f->fy) || !(fabs(f->cx) <= 8192.0) || !(fabs(f->cy) <= 8192.0),
             "intrinsics out of range");
+    for (int i = 0; i < 4; ++i) {
+        f->sT[i] = f->fx * Tinv[i];
+        f->sT[4 + i] = f->fy * Tinv[4 + i];
+    }
+    f->cxm = f->cx + FIX_MAGIC;
+    f->cym = f->cy + FIX_MAGIC;
     f->trunc = g.trunc;
     f->neg_trunc = -g.trunc;
     f->obs = obs;

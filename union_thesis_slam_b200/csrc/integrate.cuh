@@ -60,22 +60,24 @@ struct Staged {
 //   never touches rec (used by the hash map to decide whether a block needs storage).
 //   FULL = true: all four voxels exist (nvalid is ignored and the masking disappears).
 template <bool UNIT_W, bool PROBE, bool STAGED, bool FULL>
-__device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double cX, double cY, double cZ,
-                                                   const double wz[4], int nvalid, float *rec, Staged *st, int h)
+__device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double wx, double wy, double cXs, double cYs,
+                                                   double cZ, const double wz[4], int nvalid, float *rec, Staged *st,
+                                                   int h)
 {
     double Z[4];
     int pix[4];
-    bool cand[4], exact[4];
+    bool cand[4], dirty[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        Z[e] = project_fast(f, cX, cY, cZ, wz[e], pix[e], cand[e], exact[e]);
-        if (!FULL && e >= nvalid) { cand[e] = false; exact[e] = false; pix[e] = 0; }
+        Z[e] = project_fast(f, cXs, cYs, cZ, wz[e], pix[e], cand[e], dirty[e]);
+        if (!FULL && e >= nvalid) { cand[e] = false; dirty[e] = false; pix[e] = 0; }
     }
-    if (exact[0] || exact[1] || exact[2] || exact[3]) { // ~2^-15 of the voxels
+    if (dirty[0] || dirty[1] || dirty[2] || dirty[3]) { // ~2^-15 of the voxels, plus any voxel with Z <= 0
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (exact[e]) {
-                const int p = exact_pixel(f.T[2], f.T[3], f.T[6], f.T[7], cX, cY, wz[e], Z[e], f.fx, f.fy, f.cx, f.cy, f.W, f.H);
+            if (dirty[e] && Z[e] > 0.0) { // grid_fusion.py:277
+                const int p = exact_pixel(f.T[0], f.T[1], f.T[2], f.T[3], f.T[4], f.T[5], f.T[6], f.T[7], wx, wy, wz[e], Z[e],
+                                          f.fx, f.fy, f.cx, f.cy, f.W, f.H);
                 if (p >= 0) { pix[e] = p; cand[e] = true; }
             }
     }
@@ -160,9 +162,9 @@ __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, cons
                                                       int gz0, float *rec, Staged *st = nullptr)
 {
     const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
-    const double cX = __fma_rn(f.T[1], wy, __dmul_rn(f.T[0], wx));
-    const double cY = __fma_rn(f.T[5], wy, __dmul_rn(f.T[4], wx));
-    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx));
+    const double cZ = __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx)); // exact dgemm partial sum of the Z row
+    const double cXs = __fma_rn(f.sT[1], wy, __fma_rn(f.sT[0], wx, f.sT[3]));
+    const double cYs = __fma_rn(f.sT[5], wy, __fma_rn(f.sT[4], wx, f.sT[7]));
     unsigned n = 0;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -173,9 +175,9 @@ __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, cons
         const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz) + 1);
         const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
         if (nvalid >= 4)
-            n += integrate_quad<UNIT_W, PROBE, STAGED, true>(f, cX, cY, cZ, wz, 4, rec + 4 * h, st, h);
+            n += integrate_quad<UNIT_W, PROBE, STAGED, true>(f, wx, wy, cXs, cYs, cZ, wz, 4, rec + 4 * h, st, h);
         else
-            n += integrate_quad<UNIT_W, PROBE, STAGED, false>(f, cX, cY, cZ, wz, nvalid, rec + 4 * h, st, h);
+            n += integrate_quad<UNIT_W, PROBE, STAGED, false>(f, wx, wy, cXs, cYs, cZ, wz, nvalid, rec + 4 * h, st, h);
     }
     return n;
 }
