@@ -141,6 +141,22 @@ int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, int64_t *remo
 int vh_sync(tsdf_hash *h);
 int vh_last_kernel_ms(tsdf_hash *h, float *ms);
 
+/* ---------------------------------------------------------------------------------------------
+ * Surface extraction for get_mesh / get_point_cloud (grid_fusion.py:322-360,
+ * hash_fusion.py:465-507: marching cubes at level 0 on the volume get_volume() returns, vertex
+ * colours looked up at round(vertex)).  d_tsdf / d_color: dense C-order [X][Y][Z] float32 planes in
+ * DEVICE memory (tsdf_grid_download_device / vh_to_dense_device); d_color may be NULL.
+ * Vertices are world coordinates (voxel index * voxel_size + origin), one per crossed grid edge,
+ * faces index them; normals are unit TSDF gradients; colours are r, g, b bytes.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct tsdf_mesh tsdf_mesh;
+int tsdf_mesh_extract(const float *d_tsdf, const float *d_color, const int64_t dim[3], double voxel_size,
+                      const float origin[3], int device, tsdf_mesh **out, int64_t *n_verts, int64_t *n_faces);
+/* verts[n_verts][3] float32, faces[n_faces][3] int32, norms[n_verts][3] float32, colors[n_verts][3]
+ * uint8; host pointers, any may be NULL. */
+int tsdf_mesh_download(tsdf_mesh *m, float *verts, int32_t *faces, float *norms, uint8_t *colors);
+int tsdf_mesh_destroy(tsdf_mesh *m);
+
 #ifdef __cplusplus
 }
 #endif

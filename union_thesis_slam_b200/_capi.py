@@ -47,6 +47,9 @@ SYMBOLS = [
     ("vh_remove_blocks", _i, [_p, _p, _i64, _p]),
     ("vh_sync", _i, [_p]),
     ("vh_last_kernel_ms", _i, [_p, _p]),
+    ("tsdf_mesh_extract", _i, [_p, _p, _p, _d, _p, _i, _pp, _p, _p]),
+    ("tsdf_mesh_download", _i, [_p, _p, _p, _p, _p]),
+    ("tsdf_mesh_destroy", _i, [_p]),
 ]
 
 _lib = None

@@ -170,17 +170,28 @@ class TSDFVolume:
         _capi.check(self._lib.tsdf_grid_stream(self._handle, C.byref(s)))
         return s.value or 0
 
+    def _device_volume(self, dev):
+        """(tsdf, color) float32 [X,Y,Z] torch tensors on the device (all ranks' sheets when sharded)."""
+        import torch
+        shape = (len(self._local_x), int(self._vol_dim[1]), int(self._vol_dim[2]))
+        out = []
+        for which in (0, 2):
+            loc = torch.empty(shape, dtype=torch.float32, device=dev)
+            args = [None, None, None]
+            args[which] = _capi.ptr(loc)
+            _capi.check(self._lib.tsdf_grid_download_device(self._handle, *args))
+            out.append(dist.gather_x_sheets(loc, int(self._vol_dim[0]), self.rank, self.world_size, self._group))
+        return out[0], out[1]
+
     def get_point_cloud(self):
-        """Surface points with colours (reference grid_fusion.py:322-341)."""
+        """Surface points with colours, (n, 6) [x y z r g b] (reference grid_fusion.py:322-341)."""
         from . import meshing
-        tsdf_vol, color_vol = self.get_volume()
-        return meshing.point_cloud(tsdf_vol, color_vol, self._voxel_size, self._vol_origin, self._color_const)
+        return meshing.point_cloud(self)
 
     def get_mesh(self):
-        """Marching-cubes mesh (reference grid_fusion.py:343-360)."""
+        """Marching-cubes mesh: verts, faces, norms, colors (reference grid_fusion.py:343-360)."""
         from . import meshing
-        tsdf_vol, color_vol = self.get_volume()
-        return meshing.mesh(tsdf_vol, color_vol, self._voxel_size, self._vol_origin, self._color_const)
+        return meshing.mesh(self)
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle:

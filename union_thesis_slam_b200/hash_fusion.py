@@ -163,17 +163,29 @@ class HashTable:
         _capi.check(self._lib.vh_last_kernel_ms(self._handle, C.byref(ms)))
         return ms.value
 
+    def _device_volume(self, dev):
+        """(tsdf, color) float32 [X,Y,Z] torch tensors on the device (union over ranks when sharded)."""
+        import torch
+        shape = tuple(int(d) for d in self._vol_dim)
+        t = torch.empty(shape, dtype=torch.float32, device=dev)
+        c = torch.empty(shape, dtype=torch.float32, device=dev)
+        if self.world_size == 1:
+            _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), None, _capi.ptr(c)))
+            return t, c
+        w = torch.empty(shape, dtype=torch.float32, device=dev)
+        _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
+        t, w, c = dist.merge_disjoint_volumes(t, w, c, self._group)
+        return t, c
+
     def get_mesh(self):
         """Marching-cubes mesh of the scattered volume (reference hash_fusion.py:465-485)."""
         from . import meshing
-        t, c = self.get_volume()
-        return meshing.mesh(t, c, self._voxel_size, self._vol_origin, self._color_const)
+        return meshing.mesh(self)
 
     def get_point_cloud(self):
         """Surface points with colours (reference hash_fusion.py:487-507)."""
         from . import meshing
-        t, c = self.get_volume()
-        return meshing.point_cloud(t, c, self._voxel_size, self._vol_origin, self._color_const)
+        return meshing.point_cloud(self)
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle:

@@ -1,39 +1,51 @@
-"""get_mesh / get_point_cloud support (reference grid_fusion.py:322-360, hash_fusion.py:465-507).
+"""get_mesh / get_point_cloud (reference grid_fusion.py:322-360, hash_fusion.py:465-507).
 
-The reference delegates to ``skimage.measure.marching_cubes_lewiner`` (removed from scikit-image
->= 0.19 and absent from this image); no reference test or fixture pins mesh output.  Surface
-extraction is outside the integration hot path.  When scikit-image is
-importable its marching cubes is used on the downloaded volume; otherwise these calls raise.
+The reference delegates to ``skimage.measure.marching_cubes_lewiner`` (absent from this image and
+removed from scikit-image >= 0.19; no reference test or fixture pins mesh output -- mesh parity is
+unpinned).  Here marching cubes runs on the device (csrc/mesh_kernels.cu) on the same dense
+tsdf / colour volumes ``get_volume()`` returns, without moving them to the host: level 0, one
+vertex per crossed grid edge, colours looked up at ``round(vertex)`` exactly like the reference.
 """
+import ctypes as C
+
 import numpy as np
 
+from . import _capi
 
-def _marching_cubes(tsdf_vol):
+
+def extract(d_tsdf, d_color, dims, voxel_size, vol_origin, device=0):
+    """d_tsdf / d_color: device float32 [X,Y,Z] tensors (or raw pointers).  Returns
+    (verts (n,3) float32 world, faces (m,3) int32, norms (n,3) float32, colors (n,3) uint8 rgb)."""
+    lib = _capi.lib()
+    dim = np.ascontiguousarray(dims, dtype=np.int64)
+    origin = np.ascontiguousarray(vol_origin, dtype=np.float32)
+    handle, nv, nf = C.c_void_p(), C.c_int64(), C.c_int64()
+    _capi.check(lib.tsdf_mesh_extract(_capi.ptr(d_tsdf), _capi.ptr(d_color), _capi.ptr(dim), float(voxel_size),
+                                      _capi.ptr(origin), int(device), C.byref(handle), C.byref(nv), C.byref(nf)))
     try:
-        from skimage import measure
-    except ImportError as exc:
-        raise RuntimeError("get_mesh/get_point_cloud need scikit-image's marching cubes, which is not "
-                           "installed; the TSDF volume itself is available from get_volume()") from exc
-    fn = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
-    return fn(tsdf_vol, level=0)
+        verts = np.empty((nv.value, 3), np.float32)
+        faces = np.empty((nf.value, 3), np.int32)
+        norms = np.empty((nv.value, 3), np.float32)
+        colors = np.empty((nv.value, 3), np.uint8)
+        _capi.check(lib.tsdf_mesh_download(handle, _capi.ptr(verts), _capi.ptr(faces), _capi.ptr(norms),
+                                           _capi.ptr(colors)))
+    finally:
+        lib.tsdf_mesh_destroy(handle)
+    return verts, faces, norms, colors
 
 
-def _vertex_colors(color_vol, verts, color_const):
-    ind = np.round(verts).astype(int)
-    rgb = color_vol[ind[:, 0], ind[:, 1], ind[:, 2]]
-    b = np.floor(rgb / color_const)
-    g = np.floor((rgb - b * color_const) / 256)
-    r = rgb - b * color_const - g * 256
-    return np.floor(np.asarray([r, g, b])).T.astype(np.uint8)
+def mesh_of(volume):
+    """volume: TSDFVolume or HashTable.  The dense planes are produced on the device."""
+    import torch
+    dev = torch.device("cuda", volume.device)
+    t, c = volume._device_volume(dev)
+    return extract(t, c, volume._vol_dim, volume._voxel_size, volume._vol_origin, volume.device)
 
 
-def mesh(tsdf_vol, color_vol, voxel_size, vol_origin, color_const=65536):
-    verts, faces, norms, _ = _marching_cubes(tsdf_vol)
-    colors = _vertex_colors(color_vol, verts, color_const)
-    return verts * voxel_size + vol_origin, faces, norms, colors
+def mesh(volume):
+    return mesh_of(volume)
 
 
-def point_cloud(tsdf_vol, color_vol, voxel_size, vol_origin, color_const=65536):
-    verts = _marching_cubes(tsdf_vol)[0]
-    colors = _vertex_colors(color_vol, verts, color_const)
-    return np.hstack([verts * voxel_size + vol_origin, colors])
+def point_cloud(volume):
+    verts, _, _, colors = mesh_of(volume)
+    return np.hstack([verts, colors])
