@@ -276,7 +276,7 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
 
-    if rank == 0 and not args.no_hash:
+    if rank == 0 and world == 1 and not args.no_hash:
         try:
             vol.close()
             del d_frames

@@ -64,6 +64,13 @@ int tsdf_grid_destroy(tsdf_grid *g);
 /* TSDFVolume.integrate (grid_fusion.py:214-314, CPU branch semantics) -- HOST frame buffers. */
 int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const double *depth, int H, int W,
                         const double K[9], const double Tinv[16], double obs_weight);
+/* Frame ingest (grid_demo1.py:80-84): raw uint16 sensor depth.  The device computes
+ * depth = (double)raw / depth_scale (IEEE division, bit-identical to `astype(float); /= 1000.`) and
+ * maps raw == invalid_raw to 0 (`depth_im[depth_im == 65.535] = 0` for invalid_raw = 65535; pass -1
+ * to disable).  1.54 MB instead of 3.38 MB per 640x480 frame over PCIe. */
+int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W,
+                            const double K[9], const double Tinv[16], double obs_weight, double depth_scale,
+                            int invalid_raw);
 /* Same, frame already resident in device memory (throughput runs; no H2D inside). */
 int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W,
                                const double K[9], const double Tinv[16], double obs_weight);
@@ -112,6 +119,8 @@ int vh_destroy(tsdf_hash *h);
 /* HashTable.integrate (hash_fusion.py:103-145).  obs_weight follows the dense rule. */
 int vh_integrate(tsdf_hash *h, const uint8_t *rgb, const double *depth, int H, int W,
                  const double K[9], const double Tinv[16], double obs_weight);
+int vh_integrate_u16(tsdf_hash *h, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W, const double K[9],
+                     const double Tinv[16], double obs_weight, double depth_scale, int invalid_raw);
 int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,
                         const double K[9], const double Tinv[16], double obs_weight);
 

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("tsdf_grid_create", _i, [_p, _p, _d, _d, _i, _i, _i, _pp]),
     ("tsdf_grid_destroy", _i, [_p]),
     ("tsdf_grid_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
+    ("tsdf_grid_integrate_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
     ("tsdf_grid_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("tsdf_grid_download", _i, [_p, _p, _p, _p]),
     ("tsdf_grid_download_device", _i, [_p, _p, _p, _p]),
@@ -38,6 +39,7 @@ SYMBOLS = [
     ("vh_create", _i, [_p, _p, _d, _d, _i64, _i64, _i, _i, _i, _pp]),
     ("vh_destroy", _i, [_p]),
     ("vh_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
+    ("vh_integrate_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
     ("vh_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("vh_stats", _i, [_p, _p]),
     ("vh_num_blocks", _i, [_p, _p]),

@@ -176,6 +176,8 @@ int FrameIO::ensure(int npix)
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
         if (h_depth[i]) cudaFreeHost(h_depth[i]);
         if (cfold_slot[i]) cudaFree(cfold_slot[i]);
+        if (d_depth16[i]) cudaFree(d_depth16[i]);
+        d_depth16[i] = nullptr;
         d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr; cfold_slot[i] = nullptr;
     }
     d_cfold = nullptr;
@@ -186,6 +188,7 @@ int FrameIO::ensure(int npix)
         CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMallocHost(&h_depth[i], (size_t)npix * sizeof(double)));
         CUDA_TRY(cudaMalloc(&cfold_slot[i], (size_t)npix * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d_depth16[i], (size_t)npix * sizeof(uint16_t)));
     }
     cap_pix = npix;
     return TSDF_OK;
@@ -265,6 +268,37 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     return TSDF_OK;
 }
 
+int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix, double depth_scale, int invalid_raw,
+                        const uint8_t **d_rgb_out, const double **d_depth_out)
+{
+    int rc = ensure(npix);
+    if (rc) return rc;
+    const int s = next;
+    next ^= 1;
+    const bool pinned = is_pinned_host(rgb) && is_pinned_host(depth_raw);
+    const uint8_t *src_rgb = rgb;
+    const uint16_t *src_depth = depth_raw;
+    if (!pinned) {
+        CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+        memcpy(h_rgb[s], rgb, (size_t)npix * 3);
+        memcpy(h_depth[s], depth_raw, (size_t)npix * sizeof(uint16_t)); // the float64 staging buffer is large enough
+        src_rgb = h_rgb[s];
+        src_depth = reinterpret_cast<const uint16_t *>(h_depth[s]);
+    }
+    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
+    CUDA_TRY(cudaMemcpyAsync(d_depth16[s], src_depth, (size_t)npix * sizeof(uint16_t), cudaMemcpyHostToDevice, copy));
+    CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
+    CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
+    CUDA_TRY(cudaStreamWaitEvent(pre, h2d_done[s], 0));
+    if (pinned) CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+    launch_depth_u16(d_depth16[s], d_depth[s], npix, depth_scale, invalid_raw, pre);
+    CUDA_TRY(cudaGetLastError());
+    cur = s;
+    *d_rgb_out = d_rgb[s];
+    *d_depth_out = d_depth[s];
+    return TSDF_OK;
+}
+
 int FrameIO::begin_kernels()
 {
     slot ^= 1;
@@ -336,6 +370,7 @@ void FrameIO::release()
     for (int i = 0; i < 2; ++i) {
         if (cfold_slot[i]) cudaFree(cfold_slot[i]);
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
+        if (d_depth16[i]) cudaFree(d_depth16[i]);
         if (pre_done[i]) cudaEventDestroy(pre_done[i]);
         if (int_done[i]) cudaEventDestroy(int_done[i]);
         if (d_rgb[i]) cudaFree(d_rgb[i]);
@@ -502,6 +537,23 @@ extern "C" int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const doubl
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = g->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
+    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+}
+
+extern "C" int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W,
+                                       const double K[9], const double Tinv[16], double obs_weight,
+                                       double depth_scale, int invalid_raw)
+{
+    BAD_ARG(!g || !rgb || !depth_raw, "NULL argument");
+    BAD_ARG(!(depth_scale > 0.0), "depth_scale must be positive");
+    CUDA_TRY(cudaSetDevice(g->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const uint8_t *d_rgb;
+    const double *d_depth;
+    if ((rc = g->io.upload_u16(rgb, depth_raw, H * W, depth_scale, invalid_raw, &d_rgb, &d_depth))) return rc;
     return grid_run(g, d_rgb, d_depth, H, W, f, c);
 }
 

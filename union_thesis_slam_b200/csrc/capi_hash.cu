@@ -220,6 +220,23 @@ extern "C" int vh_integrate(tsdf_hash *h, const uint8_t *rgb, const double *dept
     return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
 }
 
+extern "C" int vh_integrate_u16(tsdf_hash *h, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W,
+                                const double K[9], const double Tinv[16], double obs_weight, double depth_scale,
+                                int invalid_raw)
+{
+    BAD_ARG(!h || !rgb || !depth_raw, "NULL argument");
+    BAD_ARG(!(depth_scale > 0.0), "depth_scale must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const uint8_t *d_rgb;
+    const double *d_depth;
+    if ((rc = h->io.upload_u16(rgb, depth_raw, H * W, depth_scale, invalid_raw, &d_rgb, &d_depth))) return rc;
+    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+}
+
 extern "C" int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,
                                    const double K[9], const double Tinv[16], double obs_weight)
 {

@@ -58,6 +58,17 @@ __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__re
     }
 }
 
+// Frame ingest (grid_demo1.py:81-83): depth = raw.astype(float) / depth_scale, raw == invalid_raw -> 0.
+// IEEE division, so the result is bit-identical to NumPy's.
+__global__ void k_depth_u16(const uint16_t *__restrict__ raw, double *__restrict__ depth, int npix, double scale,
+                            int invalid_raw)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int r = raw[p];
+        depth[p] = (r == invalid_raw) ? 0.0 : __ddiv_rn((double)r, scale);
+    }
+}
+
 // One thread per local brick; visible bricks are appended with one atomic per warp.
 __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, int nbz, int rank, int world,
                               BrickRef *__restrict__ list, FrameScratch *fs)
@@ -223,6 +234,11 @@ void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold,
 {
     const int warps = pyr.tx[0] * pyr.ty[0];
     k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, cfold, fs, pyr, H, W);
+}
+
+void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s)
+{
+    k_depth_u16<<<(npix + 255) / 256, 256, 0, s>>>(raw, depth, npix, scale, invalid_raw);
 }
 
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,

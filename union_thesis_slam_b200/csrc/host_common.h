@@ -66,6 +66,7 @@ struct FrameIO {
     double *d_depth[2] = {nullptr, nullptr};
     uint8_t *h_rgb[2] = {nullptr, nullptr};
     double *h_depth[2] = {nullptr, nullptr};
+    uint16_t *d_depth16[2] = {nullptr, nullptr}; // raw sensor depth (frame ingest path)
     // per-frame scratch, one set per frame parity: [FrameScratch | tile pyramid levels 1..3]
     // (cleared every frame), then pyramid level 0
     uint32_t *cfold_slot[2] = {nullptr, nullptr};
@@ -91,6 +92,10 @@ struct FrameIO {
     // stages the frame and makes `pre` wait for it; returns device pointers of the slot
     int upload(const uint8_t *rgb, const double *depth, int npix, const uint8_t **d_rgb_out,
                const double **d_depth_out);
+    // frame ingest: raw uint16 depth (grid_demo1.py:81-83) is uploaded as is (4x fewer bytes) and
+    // converted on the device to the float64 metres the rule consumes
+    int upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix, double depth_scale, int invalid_raw,
+                   const uint8_t **d_rgb_out, const double **d_depth_out);
     int ensure_cfold(int npix);
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
     // picks the frame's scratch slot, waits (on `pre`) until the frame two calls ago has left it,

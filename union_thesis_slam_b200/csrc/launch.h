@@ -40,6 +40,7 @@ void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold,
                        const TilePyramid &pyr, int H, int W, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         BrickRef *list, FrameScratch *fs, cudaStream_t s);
+void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,

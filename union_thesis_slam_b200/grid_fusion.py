@@ -77,6 +77,21 @@ class TSDFVolume:
             float(obs_weight)))
         self._host_cache = None
 
+    def integrate_raw(self, color_im, depth_raw, cam_intr, cam_pose, obs_weight=1., depth_scale=1000.,
+                      invalid_raw=65535):
+        """Frame ingest: ``depth_raw`` is the sensor's uint16 image (millimetres for the bundled
+        data); the division by ``depth_scale`` and the ``== invalid`` masking of the reference
+        demos (grid_demo1.py:81-83) happen on the device, bit-identically."""
+        im_h, im_w = depth_raw.shape
+        rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
+        raw = np.ascontiguousarray(depth_raw, dtype=np.uint16)
+        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
+        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))
+        _capi.check(self._lib.tsdf_grid_integrate_u16(
+            self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            float(obs_weight), float(depth_scale), int(invalid_raw)))
+        self._host_cache = None
+
     def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
         """Frame already resident in HBM (torch uint8 [H,W,3] / float64 [H,W] tensors or raw
         device pointers); ``tinv`` is the host-computed inverse pose."""
