@@ -183,3 +183,41 @@ def test_bad_arguments_raise():
         _gpu_volume(np.zeros((2, 3)), 0.02)
     with pytest.raises(_capi.TSDFError):
         _gpu_volume(case["vol_bnds"].copy(), 0.02, rank=3, world_size=2)
+
+
+def test_degenerate_frames_touch_nothing_and_odd_image_sizes():
+    """All-invalid depth, a camera looking away from the volume, and an image whose sides are not
+    multiples of the 8-pixel tiles."""
+    case = scenes.small_case(111, dims=(30, 22, 26), voxel_size=0.02, nframes=3, hw=(50, 70))
+    vol = _gpu_volume(case["vol_bnds"].copy(), 0.02)
+    orc = oracle.OracleTSDFVolume(case["vol_bnds"].copy(), 0.02)
+    c, d, p, _ = case["frames"][0]
+    vol.integrate(c, np.zeros_like(d), case["K"], p)
+    assert vol.stats()["updated_last"] == 0 and vol.stats()["bricks_visited_last"] == 0
+    away = p.copy()
+    away[:3, :3] = away[:3, :3] @ np.diag([1.0, -1.0, -1.0])  # rotate 180 degrees about the camera x axis
+    vol.integrate(c, d, case["K"], away)
+    orc.integrate(c, d, case["K"], away)
+    assert vol.stats()["updated_last"] == orc.updates_per_frame[-1]
+    for c, d, p, obs in case["frames"]:
+        vol.integrate(c, d, case["K"], p, obs_weight=obs)
+        n = orc.integrate(c, d, case["K"], p, obs_weight=obs)
+        assert vol.stats()["updated_last"] == n
+    assert_parity(_state(vol), (orc._tsdf_vol_cpu, orc._weight_vol_cpu, orc._color_vol_cpu))
+
+
+def test_camera_inside_volume_near_plane_voxels():
+    """Voxels a few millimetres in front of / behind the camera plane: Z <= 0 rejects, tiny Z gives huge
+    pixel coordinates (the fixed-point fast path must hand those to the exact path or reject them)."""
+    case = scenes.small_case(112, dims=(48, 40, 44), voxel_size=0.01, nframes=4, inside=True, hw=(96, 128))
+    vol = _gpu_volume(case["vol_bnds"].copy(), 0.01)
+    orc = oracle.OracleTSDFVolume(case["vol_bnds"].copy(), 0.01)
+    for c, d, p, obs in case["frames"]:
+        # put the camera centre exactly on a lattice plane so that some voxels have Z == 0 or ~1e-17
+        p = p.copy()
+        p[:3, 3] = np.float32(case["vol_bnds"][:, 0]) + 0.01 * np.round((p[:3, 3] - case["vol_bnds"][:, 0]) / 0.01)
+        p[:3, :3] = np.eye(3)
+        vol.integrate(c, d, case["K"], p, obs_weight=obs)
+        n = orc.integrate(c, d, case["K"], p, obs_weight=obs)
+        assert vol.stats()["updated_last"] == n
+    assert_parity(_state(vol), (orc._tsdf_vol_cpu, orc._weight_vol_cpu, orc._color_vol_cpu))
