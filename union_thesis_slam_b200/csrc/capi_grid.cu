@@ -119,6 +119,7 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     f->neg_trunc = -g.trunc;
     f->obs = obs;
     f->obs_f = (float)obs;
+    f->k23 = 0x4B000000u;
     f->fast_w = ((double)(float)obs == obs && obs >= 0.0009765625 && obs <= 1024.0) ? 1 : 0;
     f->unit_w = 0; // set by the handle, which knows the history of obs_weight
     f->H = H;
