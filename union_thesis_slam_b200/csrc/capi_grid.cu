@@ -390,6 +390,37 @@ void FrameIO::release()
     if (pre) cudaStreamDestroy(pre);
 }
 
+int CounterStore::init(int n_warps)
+{
+    n = n_warps;
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&frame[i], (size_t)n * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(frame[i], 0, (size_t)n * sizeof(unsigned long long)));
+    }
+    CUDA_TRY(cudaMalloc(&total, (size_t)n * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(total, 0, (size_t)n * sizeof(unsigned long long)));
+    return TSDF_OK;
+}
+
+void CounterStore::release()
+{
+    for (int i = 0; i < 2; ++i)
+        if (frame[i]) cudaFree(frame[i]);
+    if (total) cudaFree(total);
+}
+
+int CounterStore::sums(int slot, unsigned long long *last, unsigned long long *all) const
+{
+    std::vector<unsigned long long> a((size_t)n), b((size_t)n);
+    CUDA_TRY(cudaMemcpy(a.data(), frame[slot], a.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(b.data(), total, b.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long sa = 0, sb = 0;
+    for (int i = 0; i < n; ++i) { sa += a[i]; sb += b[i]; }
+    *last = sa;
+    *all = sb;
+    return TSDF_OK;
+}
+
 int tsdf_select_device(int device, int *sm_count)
 {
     int n = 0;
@@ -423,6 +454,7 @@ struct tsdf_grid {
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
+    CounterStore counters;
     bool profile_stages = false;
     bool unit_w = true; // every frame so far had obs_weight == 1 (weights are integers)
 };
@@ -437,6 +469,7 @@ static int grid_free(tsdf_grid *g)
     for (int i = 0; i < 2; ++i)
         if (g->vis_list[i]) cudaFree(g->vis_list[i]);
     if (g->tot) cudaFree(g->tot);
+    g->counters.release();
     delete g;
     return TSDF_OK;
 }
@@ -489,6 +522,10 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     // the persistent integrate grid leaves INTEGRATE_RESERVE_CTAS CTA slots per SM free so that the
     // next frame's preparation kernels (other stream) can run beside it
     g->integrate_grid = sm * std::max(1, integrate_dense_ctas_per_sm() - integrate_reserve_ctas());
+    if ((rc = g->counters.init(g->integrate_grid * (INTEGRATE_THREADS / 32)))) {
+        grid_free(g);
+        return rc;
+    }
     e = cudaStreamSynchronize(g->io.compute);
     if (e != cudaSuccess) {
         tsdf_set_error("grid initialisation failed: %s", cudaGetErrorString(e));
@@ -519,7 +556,8 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     if ((rc = g->io.prepared())) return rc;
     // integration (stream `compute`)
     if (g->profile_stages && (rc = g->io.mark())) return rc;
-    launch_integrate_dense(f, g->geom.params(), list, g->bricks, g->io.fs, g->tot, g->integrate_grid, g->io.compute);
+    launch_integrate_dense(f, g->geom.params(), list, g->bricks, g->io.fs, g->tot, g->counters.view(g->io.slot),
+                           g->integrate_grid, g->io.compute);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
     g->frames++;
@@ -632,8 +670,13 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
     Totals tot;
     if (g->io.fs) CUDA_TRY(cudaMemcpy(&fs, g->io.fs, sizeof(fs), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&tot, g->tot, sizeof(tot), cudaMemcpyDeviceToHost));
-    counters[0] = (int64_t)fs.updated;
-    counters[1] = (int64_t)tot.updated;
+    unsigned long long last = 0, all = 0;
+    if (g->frames > 0) {
+        const int rc = g->counters.sums(g->io.slot, &last, &all);
+        if (rc) return rc;
+    }
+    counters[0] = (int64_t)last;
+    counters[1] = (int64_t)all;
     counters[2] = (int64_t)tot.last_visited;
     counters[3] = g->frames;
     return TSDF_OK;

@@ -14,6 +14,7 @@ struct tsdf_hash {
     BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity
     Totals *tot = nullptr;
     int *scratch_count = nullptr; // device int used by export / remove
+    CounterStore counters;
     uint32_t *sb_flags = nullptr; // per-frame bitmap of super-blocks touched by the ray walk
     size_t sb_words = 0;
     int integrate_grid = 0;
@@ -32,6 +33,7 @@ static int hash_free(tsdf_hash *h)
                     h->dev.blocks, h->dev.known, h->vis_list[0], h->vis_list[1], h->tot, h->scratch_count, h->sb_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    h->counters.release();
     delete h;
     return TSDF_OK;
 }
@@ -99,6 +101,10 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
     cudaMemsetAsync(h->tot, 0, sizeof(Totals), h->io.compute);
     launch_hash_init(d, sm, h->io.compute);
     h->integrate_grid = sm * std::max(1, integrate_hash_ctas_per_sm() - integrate_reserve_ctas());
+    if ((rc = h->counters.init(h->integrate_grid * (INTEGRATE_THREADS / 32)))) {
+        hash_free(h);
+        return rc;
+    }
     e = cudaStreamSynchronize(h->io.compute);
     if (e != cudaSuccess) {
         tsdf_set_error("hash map initialisation failed: %s", cudaGetErrorString(e));
@@ -198,7 +204,8 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
                            list, h->io.fs, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.prepared())) return rc;
-    launch_integrate_hash(f, h->geom.params(), h->dev, list, h->io.fs, h->tot, h->integrate_grid, h->io.compute);
+    launch_integrate_hash(f, h->geom.params(), h->dev, list, h->io.fs, h->tot, h->counters.view(h->io.slot),
+                          h->integrate_grid, h->io.compute);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.end_kernels())) return rc;
     h->frames++;
@@ -267,8 +274,13 @@ extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
     stats[2] = h->table_slots;
     stats[3] = h->heap_blocks;
     stats[4] = heap_top;
-    stats[5] = (int64_t)fs.updated;
-    stats[6] = (int64_t)tot.updated;
+    unsigned long long last = 0, all = 0;
+    if (h->frames > 0) {
+        const int rc = h->counters.sums(h->io.slot, &last, &all);
+        if (rc) return rc;
+    }
+    stats[5] = (int64_t)last;
+    stats[6] = (int64_t)all;
     stats[7] = (int64_t)tot.last_visited;
     stats[8] = (int64_t)tot.max_probe;
     stats[9] = fs.new_keys;

@@ -113,7 +113,7 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
-                  FrameScratch *fs, Totals *tot)
+                  FrameScratch *fs, Totals *tot, UpdateCounters uc)
 {
     __shared__ __align__(128) float s_rec[2][BRICK_FLOATS];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -157,9 +157,10 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         if (!st.waited) mbar_wait(st.bar, st.parity);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
-    if ((t & 31) == 0 && my_updates) {
-        atomicAdd(&fs->updated, (unsigned long long)my_updates);
-        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    if ((t & 31) == 0) { // one private slot per warp: no atomics
+        const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
+        uc.frame[w] = my_updates;
+        uc.total[w] += my_updates;
     }
     if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
@@ -170,7 +171,7 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
-                  FrameScratch *fs, Totals *tot)
+                  FrameScratch *fs, Totals *tot, UpdateCounters uc)
 {
     const int n = fs->vis_count;
     const int t = threadIdx.x;
@@ -194,9 +195,10 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
                                                        bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
-    if ((t & 31) == 0 && my_updates) {
-        atomicAdd(&fs->updated, (unsigned long long)my_updates);
-        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    if ((t & 31) == 0) { // one private slot per warp: no atomics
+        const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
+        uc.frame[w] = my_updates;
+        uc.total[w] += my_updates;
     }
     if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
@@ -262,12 +264,12 @@ int integrate_dense_ctas_per_sm()
 }
 
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
-                            FrameScratch *fs, Totals *tot, int grid, cudaStream_t s)
+                            FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s)
 {
     if (f.unit_w)
-        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
+        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot, uc);
     else
-        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot);
+        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot, uc);
 }
 
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,

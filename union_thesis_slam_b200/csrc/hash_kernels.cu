@@ -234,7 +234,8 @@ __global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickR
 // K5: per-block integration.
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
-k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__restrict__ list, FrameScratch *fs, Totals *tot)
+k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__restrict__ list, FrameScratch *fs, Totals *tot,
+                 UpdateCounters uc)
 {
     __shared__ uint32_t s_storage;
     const int n = fs->vis_count;
@@ -287,9 +288,10 @@ k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__res
                                                            h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t);
     }
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
-    if ((t & 31) == 0 && my_updates) {
-        atomicAdd(&fs->updated, (unsigned long long)my_updates);
-        atomicAdd(&tot->updated, (unsigned long long)my_updates);
+    if ((t & 31) == 0) { // one private slot per warp: no atomics
+        const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
+        uc.frame[w] = my_updates;
+        uc.total[w] += my_updates;
     }
     if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
@@ -420,12 +422,12 @@ int integrate_hash_ctas_per_sm()
 }
 
 void launch_integrate_hash(const FrameParams &f, const VolumeParams &v, const HashDev &h, const BrickRef *list,
-                           FrameScratch *fs, Totals *tot, int grid, cudaStream_t s)
+                           FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s)
 {
     if (f.unit_w)
-        k_integrate_hash<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot);
+        k_integrate_hash<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot, uc);
     else
-        k_integrate_hash<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot);
+        k_integrate_hash<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, h, list, fs, tot, uc);
 }
 
 void launch_scatter_dense(const HashDev &h, int dim_x, int dim_y, int dim_z, float *tsdf, float *wgt, float *col,

@@ -49,6 +49,17 @@ struct VolumeGeom {
 };
 
 int tsdf_select_device(int device, int *sm_count);
+
+// Per-warp update counters owned by a handle (see UpdateCounters).
+struct CounterStore {
+    unsigned long long *frame[2] = {nullptr, nullptr}; // one per frame parity
+    unsigned long long *total = nullptr;
+    int n = 0;
+    int init(int n_warps);
+    void release();
+    UpdateCounters view(int slot) const { return UpdateCounters{frame[slot], total}; }
+    int sums(int slot, unsigned long long *last, unsigned long long *all) const; // after a stream sync
+};
 int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
                       const double Tinv[16], double obs);
 

@@ -27,6 +27,14 @@ struct TilePyramid {
     int tx[4], ty[4];
 };
 
+// Per-warp update counters of the integrate kernels: every warp owns one slot of each array, so
+// counting costs no atomics (thousands of same-address atomics per launch cost ~15-25 us).
+// frame[] is overwritten every frame, total[] accumulates; the host sums them when asked.
+struct UpdateCounters {
+    unsigned long long *frame;
+    unsigned long long *total;
+};
+
 // Lives for the lifetime of the handle.
 struct Totals {
     unsigned long long updated;      // voxels updated since create
@@ -44,7 +52,7 @@ void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
-                            FrameScratch *fs, Totals *tot, int grid, cudaStream_t s);
+                            FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s);
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
                     float *col, int sm_count, cudaStream_t s);
 
@@ -91,7 +99,7 @@ void launch_compact_visible(const FrameParams &f, const CullParams &c, const Has
                             BrickRef *list, FrameScratch *fs, cudaStream_t s);
 int integrate_hash_ctas_per_sm();
 void launch_integrate_hash(const FrameParams &f, const VolumeParams &v, const HashDev &h, const BrickRef *list,
-                           FrameScratch *fs, Totals *tot, int grid, cudaStream_t s);
+                           FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s);
 void launch_scatter_dense(const HashDev &h, int dim_x, int dim_y, int dim_z, float *tsdf, float *wgt, float *col,
                           int sm_count, cudaStream_t s);
 void launch_export_blocks(const HashDev &h, int capacity, int *count, int32_t *keys_out, float *payload, int sm_count,
