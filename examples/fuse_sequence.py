@@ -39,6 +39,18 @@ def read_depth(data, i):
     return depth_im
 
 
+def sequence_bounds(data, ids, cam_intr):
+    """Axis-aligned hull of every frame's view frustum (apex + image corners at the frame's largest
+    depth), starting from the origin like the reference demos do."""
+    hull = np.zeros((3, 2))
+    for i in ids:
+        pose = np.loadtxt(os.path.join(data, "frame-%06d.pose.txt" % i))
+        corners = grid_fusion.get_view_frustum(read_depth(data, i), cam_intr, pose)
+        hull[:, 0] = np.minimum(hull[:, 0], corners.min(axis=1))
+        hull[:, 1] = np.maximum(hull[:, 1], corners.max(axis=1))
+    return hull
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "frames"))
@@ -53,13 +65,7 @@ def main():
     cam_intr = np.loadtxt(os.path.join(args.data, "camera-intrinsics.txt"), delimiter=' ')
 
     print("Estimating voxel volume bounds...")
-    vol_bnds = np.zeros((3, 2))
-    for i in ids:
-        depth_im = read_depth(args.data, i)
-        cam_pose = np.loadtxt(os.path.join(args.data, "frame-%06d.pose.txt" % i))
-        view_frust_pts = grid_fusion.get_view_frustum(depth_im, cam_intr, cam_pose)
-        vol_bnds[:, 0] = np.minimum(vol_bnds[:, 0], np.amin(view_frust_pts, axis=1))
-        vol_bnds[:, 1] = np.maximum(vol_bnds[:, 1], np.amax(view_frust_pts, axis=1))
+    vol_bnds = sequence_bounds(args.data, ids, cam_intr)
 
     maps = {}
     if args.map in ("grid", "both"):
