@@ -97,6 +97,25 @@ def test_config2_three_frames():
     assert st["table_keys"] >= st["blocks"] and st["heap_free"] == st["heap_capacity"] - st["blocks"]
 
 
+def test_config2_ten_frames_equals_dense_reference_sha256():
+    """Ten bundled frames into the hash map at 2 cm: since hash and dense share their arithmetic, the
+    scattered volumes must hash to the DENSE reference digests; the block count is the reference's."""
+    G = frames.golden()
+    K = frames.intrinsics()
+    ht = _table(scenes.CONFIG1_BOUNDS, scenes.CONFIG1_VOXEL, map_size=1 << 17)
+    total = 0
+    for n, i in enumerate(range(10), 1):
+        c, d, p = frames.load_frame(i)
+        ht.integrate(c, d, K, p, obs_weight=1.)
+        total += ht.stats()["updated_last"]
+    g = G["dense"]["10"]
+    t, w, c_ = ht.get_volume_with_weight()
+    assert frames.sha(w) == g["weight"] and frames.sha(t) == g["tsdf"] and frames.sha(c_) == g["color"]
+    assert total == g["sum_w"] == 3557017
+    st = ht.stats()
+    assert st["blocks"] == g["n_blocks"] == 1511 and st["updated_total"] == 3557017
+
+
 @pytest.mark.parametrize("seed,dims,vs,kw", [
     (201, (40, 40, 40), 0.02, {}),
     (202, (7, 9, 5), 0.04, {}),
