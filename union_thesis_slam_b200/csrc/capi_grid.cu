@@ -399,6 +399,8 @@ int CounterStore::init(int n_warps)
     }
     CUDA_TRY(cudaMalloc(&total, (size_t)n * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(total, 0, (size_t)n * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d_stats, sizeof(StatsBlock)));
+    CUDA_TRY(cudaMallocHost(&h_stats, sizeof(StatsBlock)));
     return TSDF_OK;
 }
 
@@ -407,17 +409,18 @@ void CounterStore::release()
     for (int i = 0; i < 2; ++i)
         if (frame[i]) cudaFree(frame[i]);
     if (total) cudaFree(total);
+    if (d_stats) cudaFree(d_stats);
+    if (h_stats) cudaFreeHost(h_stats);
 }
 
-int CounterStore::sums(int slot, unsigned long long *last, unsigned long long *all) const
+int CounterStore::collect(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries,
+                          const int *heap_top, cudaStream_t s, const StatsBlock **out)
 {
-    std::vector<unsigned long long> a((size_t)n), b((size_t)n);
-    CUDA_TRY(cudaMemcpy(a.data(), frame[slot], a.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(b.data(), total, b.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    unsigned long long sa = 0, sb = 0;
-    for (int i = 0; i < n; ++i) { sa += a[i]; sb += b[i]; }
-    *last = sa;
-    *all = sb;
+    launch_collect_stats(view(slot), n, fs, tot, n_entries, heap_top, d_stats, s);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_stats, d_stats, sizeof(StatsBlock), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *out = h_stats;
     return TSDF_OK;
 }
 
@@ -664,20 +667,13 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
 {
     BAD_ARG(!g || !counters, "NULL argument");
     CUDA_TRY(cudaSetDevice(g->device));
-    CUDA_TRY(cudaStreamSynchronize(g->io.compute));
-    FrameScratch fs;
-    memset(&fs, 0, sizeof(fs));
-    Totals tot;
-    if (g->io.fs) CUDA_TRY(cudaMemcpy(&fs, g->io.fs, sizeof(fs), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&tot, g->tot, sizeof(tot), cudaMemcpyDeviceToHost));
-    unsigned long long last = 0, all = 0;
-    if (g->frames > 0) {
-        const int rc = g->counters.sums(g->io.slot, &last, &all);
-        if (rc) return rc;
-    }
-    counters[0] = (int64_t)last;
-    counters[1] = (int64_t)all;
-    counters[2] = (int64_t)tot.last_visited;
+    const StatsBlock *st = nullptr;
+    const int slot = g->frames > 0 ? g->io.slot : 0;
+    int rc = g->counters.collect(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, &st);
+    if (rc) return rc;
+    counters[0] = g->frames > 0 ? (int64_t)st->updated_last : 0;
+    counters[1] = (int64_t)st->updated_total;
+    counters[2] = (int64_t)st->last_visited;
     counters[3] = g->frames;
     return TSDF_OK;
 }

@@ -260,33 +260,31 @@ extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
 {
     BAD_ARG(!h || !stats, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->io.compute));
-    FrameScratch fs;
-    memset(&fs, 0, sizeof(fs));
-    Totals tot;
-    int n_entries = 0, heap_top = 0;
-    if (h->io.fs) CUDA_TRY(cudaMemcpy(&fs, h->io.fs, sizeof(fs), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&tot, h->tot, sizeof(tot), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&n_entries, h->dev.n_entries, sizeof(int), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&heap_top, h->dev.heap_top, sizeof(int), cudaMemcpyDeviceToHost));
-    stats[0] = h->heap_blocks - heap_top;
-    stats[1] = n_entries;
+    const StatsBlock *st = nullptr;
+    const int slot = h->frames > 0 ? h->io.slot : 0;
+    int rc = h->counters.collect(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.compute, &st);
+    if (rc) return rc;
+    stats[0] = h->heap_blocks - st->heap_top;
+    stats[1] = st->n_entries;
     stats[2] = h->table_slots;
     stats[3] = h->heap_blocks;
-    stats[4] = heap_top;
-    unsigned long long last = 0, all = 0;
-    if (h->frames > 0) {
-        const int rc = h->counters.sums(h->io.slot, &last, &all);
-        if (rc) return rc;
-    }
-    stats[5] = (int64_t)last;
-    stats[6] = (int64_t)all;
-    stats[7] = (int64_t)tot.last_visited;
-    stats[8] = (int64_t)tot.max_probe;
-    stats[9] = fs.new_keys;
+    stats[4] = st->heap_top;
+    stats[5] = h->frames > 0 ? (int64_t)st->updated_last : 0;
+    stats[6] = (int64_t)st->updated_total;
+    stats[7] = (int64_t)st->last_visited;
+    stats[8] = (int64_t)st->max_probe;
+    stats[9] = st->new_keys;
     stats[10] = h->frames;
-    stats[11] = fs.cand_count;
-    return check_device_error(h);
+    stats[11] = st->cand_count;
+    if (st->error) {
+        const int code = -(int)st->error;
+        tsdf_set_error(code == TSDF_ERR_HEAP_EXHAUSTED
+                           ? "voxel-block heap exhausted (%lld blocks): blocks were dropped; create the map with more heap_blocks"
+                           : "hash table full (%lld slots): keys were dropped; create the map with more table_slots",
+                       (long long)(code == TSDF_ERR_HEAP_EXHAUSTED ? h->heap_blocks : h->table_slots));
+        return code;
+    }
+    return TSDF_OK;
 }
 
 extern "C" int vh_num_blocks(tsdf_hash *h, int64_t *n)

@@ -204,6 +204,34 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
 }
 #endif
 
+// Stats read-out: sums the per-warp update counters and gathers the scalar counters into one block.
+__global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot,
+                                const int *n_entries, const int *heap_top, StatsBlock *out)
+{
+    __shared__ unsigned long long s_a[8], s_b[8];
+    unsigned long long a = 0, b = 0;
+    for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
+        a += uc.frame[i];
+        b += uc.total[i];
+    }
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_a[i]; b += s_b[i]; }
+        StatsBlock r;
+        r.updated_last = a; r.updated_total = b;
+        r.last_visited = tot->last_visited; r.max_probe = tot->max_probe; r.error = tot->error;
+        r.cand_count = fs ? fs->cand_count : 0; r.new_keys = fs ? fs->new_keys : 0; r.vis_count = fs ? fs->vis_count : 0;
+        r.n_entries = n_entries ? *n_entries : 0; r.heap_top = heap_top ? *heap_top : 0; r.pad = 0;
+        *out = r;
+    }
+}
+
 // Read-out: bricks -> C-order [n_x][Y][Z] planes (grid_fusion.py:316-320 layout).
 __global__ void k_unbrick(const float *__restrict__ bricks, int n_x, int dim_y, int dim_z, int nby, int nbz,
                           float *__restrict__ tsdf, float *__restrict__ wgt, float *__restrict__ col)
@@ -255,6 +283,12 @@ void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int
 #define INTEGRATE_RESERVE_CTAS 2
 #endif
 int integrate_reserve_ctas() { return INTEGRATE_RESERVE_CTAS; }
+
+void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
+                          const int *heap_top, StatsBlock *out, cudaStream_t s)
+{
+    k_collect_stats<<<1, 256, 0, s>>>(uc, n_warps, fs, tot, n_entries, heap_top, out);
+}
 
 int integrate_dense_ctas_per_sm()
 {

@@ -58,7 +58,10 @@ struct CounterStore {
     int init(int n_warps);
     void release();
     UpdateCounters view(int slot) const { return UpdateCounters{frame[slot], total}; }
-    int sums(int slot, unsigned long long *last, unsigned long long *all) const; // after a stream sync
+    StatsBlock *d_stats = nullptr, *h_stats = nullptr; // device block + pinned host mirror
+    // one kernel + one D2H copy + one stream sync; returns the pinned mirror
+    int collect(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries, const int *heap_top,
+                cudaStream_t s, const StatsBlock **out);
 };
 int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
                       const double Tinv[16], double obs);

@@ -35,6 +35,13 @@ struct UpdateCounters {
     unsigned long long *total;
 };
 
+// Everything the stats calls report, gathered by one small kernel and one D2H copy.
+struct StatsBlock {
+    unsigned long long updated_last, updated_total;
+    unsigned long long last_visited, max_probe, error;
+    int cand_count, new_keys, vis_count, n_entries, heap_top, pad;
+};
+
 // Lives for the lifetime of the handle.
 struct Totals {
     unsigned long long updated;      // voxels updated since create
@@ -49,6 +56,8 @@ void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold,
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         BrickRef *list, FrameScratch *fs, cudaStream_t s);
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
+void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
+                          const int *heap_top, StatsBlock *out, cudaStream_t s);
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
