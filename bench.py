@@ -295,7 +295,7 @@ def run_b200(args):
     return 0
 
 
-def bench_hash(args, dev, local, peak):
+def bench_hash(args, dev, local, peak, rank=0, world=1):
     """Voxel-block hash map, BASELINE.json configs[4]-shaped: 1280x720 synthetic depth stream on a
     seeded trajectory through a 40 x 40 x 6 m room at 2 cm voxels (8^3 blocks; the bounded block grid
     holds 2.4 M blocks), single GPU.  Frames resident in HBM; whole-pipeline device time."""
@@ -304,7 +304,9 @@ def bench_hash(args, dev, local, peak):
     room = synth.room_bounds(HASH_ROOM)
     frames, K = synth.room_stream(N_FRAMES, room, width=HASH_W, height=HASH_H, seed=1)
     nblocks = int(np.prod(np.ceil(np.array(HASH_ROOM) / HASH_VOXEL / 8)))
-    ht = hash_fusion.HashTable(room.copy(), HASH_VOXEL, map_size=4 * nblocks, heap_blocks=nblocks, device=local)
+    per_rank = int(nblocks / world * 1.25) + 1024  # owner hash balances to a few percent
+    ht = hash_fusion.HashTable(room.copy(), HASH_VOXEL, map_size=4 * per_rank, heap_blocks=per_rank, device=local,
+                               rank=rank, world_size=world)
     d_frames = [(torch.from_numpy(c).to(dev), torch.from_numpy(d).to(dev), np.linalg.inv(p)) for c, d, p in frames]
     torch.cuda.synchronize()
     steps = min(args.steps, 256)
@@ -313,17 +315,31 @@ def bench_hash(args, dev, local, peak):
         dc, dd, ti = d_frames[i % N_FRAMES]
         ht.integrate_device(dc, dd, HASH_H, HASH_W, K, ti, 1.0)
 
+    import torch.distributed as dist
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
     for i in range(max(args.warmup, N_FRAMES)):  # one full pass allocates the blocks of the trajectory
         step(i)
     ht.sync()
     s0 = ht.stats()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for i in range(steps):
         step(i)
     ht.sync()
     wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    wall = allreduce(wall, dist.ReduceOp.MAX if world > 1 else None)
     s1 = ht.stats()
-    upd = s1["updated_total"] - s0["updated_total"]
+    upd = allreduce(float(s1["updated_total"] - s0["updated_total"]), dist.ReduceOp.SUM if world > 1 else None)
     # algorithmic bytes of the same frames (second pass, per-frame counters)
     tot_bytes = 0.0
     for i in range(steps):
@@ -331,8 +347,11 @@ def bench_hash(args, dev, local, peak):
         st = ht.stats()
         tot_bytes += 24.0 * st["updated_last"] + 16.0 * (st["blocks_visited_last"] + st["keys_inserted_last"]) \
             + 12.0 * HASH_W * HASH_H
-    achieved = tot_bytes / wall / 1e9
-    return {"metric": "tsdf_voxel_updates_per_s", "value": upd / wall, "unit": "voxel-updates/s",
+    tot_bytes = allreduce(tot_bytes, dist.ReduceOp.SUM if world > 1 else None)
+    blocks_all = allreduce(float(s1["blocks"]), dist.ReduceOp.SUM if world > 1 else None)
+    achieved = tot_bytes / wall / 1e9 / world  # per GPU, against one GPU's HBM peak
+    return {"metric": "tsdf_voxel_updates_per_s", "value": upd / wall, "unit": "voxel-updates/s", "n_gpus": world,
+            "blocks_allocated_all_ranks": int(blocks_all),
             "frames_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps,
             "workload": "BASELINE.json configs[4]: 1280x720 stream, 40x40x6 m room, 2 cm voxels, 8^3 blocks",
             "voxel_size_m": HASH_VOXEL, "blocks_allocated": s1["blocks"], "table_keys": s1["table_keys"],
@@ -352,12 +371,37 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-hash", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="dense", choices=["dense", "hash"],
+                    help="hash: print the hash-map line alone (works under torchrun: blocks sharded by owner hash)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "hash":
+        return run_hash_only(args)
     return run_b200(args)
+
+
+def run_hash_only(args):
+    """Hash map alone, optionally sharded over the ranks of a torchrun launch (owner-hashed blocks,
+    every rank walks every frame, no per-frame collective)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = bench_hash(args, torch.device("cuda", local), local, peaks()[0], rank, world)
+    line.update({"higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f64"})
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 if __name__ == "__main__":
