@@ -192,7 +192,7 @@ def run_b200(args):
         dc, dd, tinv = d_frames[i % N_FRAMES]
         vol.integrate_device(dc, dd, IM_H, IM_W, K, tinv, 1.0)
 
-    launches_per_step = 3  # prep_frame, cull_bricks, integrate_dense (+ one 32-byte memset)
+    launches_per_step = 4  # prep_frame, cull_bricks, 2 x integrate_dense (+ one small memset)
     for i in range(args.warmup):
         step(i)
     vol.sync()
@@ -205,6 +205,7 @@ def run_b200(args):
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
+    vol.flush()  # the frame's second integrate kernel runs on a sibling stream: join it before the end event
     e1.record(stream)
     vol.sync()
     barrier()

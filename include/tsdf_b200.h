@@ -99,6 +99,11 @@ int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms);
 int tsdf_grid_set_profiling(tsdf_grid *g, int on);
 int tsdf_grid_last_stage_ms(tsdf_grid *g, float ms[4], int *n);
 int tsdf_grid_stream(tsdf_grid *g, void **stream);
+/* The integrate kernels of a frame run on two device streams (two independent halves of the
+ * bricks).  flush() makes the stream returned by tsdf_grid_stream() wait -- on the device, the
+ * host does not block -- for every kernel issued so far, so that an event recorded on it
+ * afterwards marks the completion of all of them.  Read-out calls and sync() do this themselves. */
+int tsdf_grid_flush(tsdf_grid *g);
 
 /* ---------------------------------------------------------------------------------------------
  * Voxel-block hash map.  Replaces hash_fusion.HashTable (hash_fusion.py:29-507) on the

@@ -18,7 +18,7 @@ for rep in range(6):
     e0.record(stream)
     for dc, dd, ti in dev:
         vol.integrate_device(dc, dd, H, W, K, ti, 1.0)
-    e1.record(stream); vol.sync()
+    vol.flush(); e1.record(stream); vol.sync()
     ms = e0.elapsed_time(e1) / len(dev); u = (vol.stats()["updated_total"] - u0) / len(dev)
     by = 24.0 * u + 12.0 * H * W
     print("rep %d: %.1f us/frame, %.3e updates/frame, %.3e voxel-updates/s, %.0f GB/s (%.1f%% of 6551)" % (

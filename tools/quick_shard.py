@@ -18,7 +18,7 @@ for rep in range(4):
     for dc, dd, ti in dev:
         vol.integrate_device(dc, dd, H, W, K, ti, 1.0)
     t_issue = time.perf_counter() - t0
-    e1.record(stream); vol.sync()
+    vol.flush(); e1.record(stream); vol.sync()
     print("rep %d: device %.1f us/frame, host issue %.1f us/frame" % (rep, 1e3 * e0.elapsed_time(e1) / nfr, 1e6 * t_issue / nfr))
 # kernel-only time of the shard's integrate kernel (serialised, per-frame sync)
 vol.set_profiling(True)

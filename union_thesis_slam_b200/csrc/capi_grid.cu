@@ -141,6 +141,7 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
 int FrameIO::init()
 {
     CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&compute2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     {   // preparation kernels are short and on the critical path of the next frame: highest priority
         int lo = 0, hi = 0;
@@ -152,9 +153,12 @@ int FrameIO::init()
         CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&pre_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&int_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&int_done2[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&slot_free2[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreate(&k_begin));
     CUDA_TRY(cudaEventCreate(&k_end));
+    CUDA_TRY(cudaEventCreate(&k_end2));
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&k_mark[i]));
     return TSDF_OK;
 }
@@ -170,6 +174,7 @@ int FrameIO::ensure(int npix)
     if (npix <= cap_pix) return TSDF_OK;
     CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
+    CUDA_TRY(cudaStreamSynchronize(compute2));
     CUDA_TRY(cudaStreamSynchronize(copy));
     for (int i = 0; i < 2; ++i) {
         if (d_rgb[i]) cudaFree(d_rgb[i]);
@@ -200,6 +205,7 @@ int FrameIO::ensure_tiles(int H, int W)
     if (scratch_slot[0] && H == tiles_H && W == tiles_W) return TSDF_OK;
     CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
+    CUDA_TRY(cudaStreamSynchronize(compute2));
     size_t off[4], total = 256; // FrameScratch lives in the first 256 bytes
     TilePyramid p{};
     for (int l = 1; l <= 3; ++l) {
@@ -257,6 +263,7 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     }
     // the device slot was last read by the kernels of the frame two calls ago
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
+    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free2[s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth[s], src_depth, (size_t)npix * sizeof(double), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -287,6 +294,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
         src_depth = reinterpret_cast<const uint16_t *>(h_depth[s]);
     }
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
+    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free2[s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth16[s], src_depth, (size_t)npix * sizeof(uint16_t), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -308,6 +316,7 @@ int FrameIO::begin_kernels()
     pyr = pyr_slot[slot];
     // the integrate kernel of the frame two calls ago was the last reader of this slot
     CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
+    CUDA_TRY(cudaStreamWaitEvent(pre, int_done2[slot], 0));
     CUDA_TRY(cudaEventRecord(k_begin, pre));
     CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
@@ -318,6 +327,16 @@ int FrameIO::prepared()
 {
     CUDA_TRY(cudaEventRecord(pre_done[slot], pre));
     CUDA_TRY(cudaStreamWaitEvent(compute, pre_done[slot], 0));
+    if (dual) CUDA_TRY(cudaStreamWaitEvent(compute2, pre_done[slot], 0));
+    return TSDF_OK;
+}
+
+int FrameIO::join()
+{
+    if (!pending2) return TSDF_OK;
+    // int_done2[slot] is the last event recorded on compute2
+    CUDA_TRY(cudaStreamWaitEvent(compute, int_done2[slot], 0));
+    pending2 = false;
     return TSDF_OK;
 }
 
@@ -346,9 +365,16 @@ int FrameIO::end_kernels()
 {
     CUDA_TRY(cudaEventRecord(k_end, compute));
     CUDA_TRY(cudaEventRecord(int_done[slot], compute));
+    end2 = dual;
+    if (dual) {
+        CUDA_TRY(cudaEventRecord(k_end2, compute2));
+        CUDA_TRY(cudaEventRecord(int_done2[slot], compute2));
+        pending2 = true;
+    }
     timed = true;
     if (cur >= 0) {
         CUDA_TRY(cudaEventRecord(slot_free[cur], compute));
+        if (dual) CUDA_TRY(cudaEventRecord(slot_free2[cur], compute2));
         cur = -1;
     }
     return TSDF_OK;
@@ -360,6 +386,12 @@ int FrameIO::last_ms(float *ms)
     BAD_ARG(!timed, "no frame integrated yet");
     CUDA_TRY(cudaEventSynchronize(k_end));
     CUDA_TRY(cudaEventElapsedTime(ms, k_begin, k_end));
+    if (end2) { // the frame's second integrate kernel ran on compute2: whichever ended last
+        float ms2 = 0.f;
+        CUDA_TRY(cudaEventSynchronize(k_end2));
+        CUDA_TRY(cudaEventElapsedTime(&ms2, k_begin, k_end2));
+        if (ms2 > *ms) *ms = ms2;
+    }
     return TSDF_OK;
 }
 
@@ -367,8 +399,11 @@ void FrameIO::release()
 {
     if (pre) cudaStreamSynchronize(pre);
     if (compute) cudaStreamSynchronize(compute);
+    if (compute2) cudaStreamSynchronize(compute2);
     if (copy) cudaStreamSynchronize(copy);
     for (int i = 0; i < 2; ++i) {
+        if (int_done2[i]) cudaEventDestroy(int_done2[i]);
+        if (slot_free2[i]) cudaEventDestroy(slot_free2[i]);
         if (cfold_slot[i]) cudaFree(cfold_slot[i]);
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
@@ -385,7 +420,9 @@ void FrameIO::release()
         if (k_mark[i]) cudaEventDestroy(k_mark[i]);
     if (k_begin) cudaEventDestroy(k_begin);
     if (k_end) cudaEventDestroy(k_end);
+    if (k_end2) cudaEventDestroy(k_end2);
     if (compute) cudaStreamDestroy(compute);
+    if (compute2) cudaStreamDestroy(compute2);
     if (copy) cudaStreamDestroy(copy);
     if (pre) cudaStreamDestroy(pre);
 }
@@ -453,7 +490,9 @@ struct tsdf_grid {
     int64_t n_x_local = 0;     // local voxel rows
     size_t nbricks = 0;
     float *bricks = nullptr;
-    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity
+    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity: [class 0 | class 1]
+    int classes = 2;           // independent checkerboard classes of bricks (1 or 2), one integrate kernel each
+    size_t list_b_off = 0;     // where the class-1 list starts inside vis_list[]
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
@@ -504,6 +543,8 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
         g->n_x_local += std::min<int64_t>(BRICK, dim[0] - x0);
     }
     g->nbricks = (size_t)g->nlbx * g->geom.nb[1] * g->geom.nb[2];
+    if (const char *e = getenv("TSDF_DENSE_CLASSES")) g->classes = atoi(e) == 1 ? 1 : 2;
+    g->list_b_off = (g->nbricks + 1) / 2; // a box's checkerboard has at most ceil(n/2) cells of class 0
     if (g->nbricks >= (size_t)1 << 31) {
         grid_free(g);
         tsdf_set_error("too many bricks per rank (%zu)", g->nbricks);
@@ -525,7 +566,7 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     // the persistent integrate grid leaves INTEGRATE_RESERVE_CTAS CTA slots per SM free so that the
     // next frame's preparation kernels (other stream) can run beside it
     g->integrate_grid = sm * std::max(1, integrate_dense_ctas_per_sm() - integrate_reserve_ctas());
-    if ((rc = g->counters.init(g->integrate_grid * (INTEGRATE_THREADS / 32)))) {
+    if ((rc = g->counters.init(g->classes * g->integrate_grid * (INTEGRATE_THREADS / 32)))) {
         grid_free(g);
         return rc;
     }
@@ -553,14 +594,26 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     f.cfold = g->io.d_cfold;
     g->unit_w = g->unit_w && f.obs == 1.0;
     f.unit_w = g->unit_w ? 1 : 0;
-    // preparation (stream `pre`, overlaps the previous frame's integrate kernel)
+    // preparation (stream `pre`, overlaps the previous frame's integrate kernels)
     launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, g->io.pre);
-    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, list, g->io.fs, g->io.pre);
+    BrickRef *list_b = list + g->list_b_off;
+    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list, list_b,
+                       g->io.fs, g->io.pre);
+    // Two independent classes of bricks, one kernel each on its own stream: kernel B's CTAs take the
+    // SM slots kernel A's tail frees, and the next frame's kernel A does the same for B, so neither
+    // the launch gap nor the drain of the persistent grids leaves the SMs idle.  With stage profiling
+    // on, both run on `compute` so that the stage marks delimit them.
+    g->io.dual = g->classes == 2 && !g->profile_stages;
+    if (!g->io.dual && (rc = g->io.join())) return rc;
     if ((rc = g->io.prepared())) return rc;
-    // integration (stream `compute`)
     if (g->profile_stages && (rc = g->io.mark())) return rc;
-    launch_integrate_dense(f, g->geom.params(), list, g->bricks, g->io.fs, g->tot, g->counters.view(g->io.slot),
-                           g->integrate_grid, g->io.compute);
+    const VolumeParams vp = g->geom.params();
+    const int warps = g->integrate_grid * (INTEGRATE_THREADS / 32);
+    launch_integrate_dense(f, vp, list, &g->io.fs->vis_count, g->bricks, g->counters.view(g->io.slot), g->integrate_grid,
+                           g->io.compute);
+    if (g->classes == 2)
+        launch_integrate_dense(f, vp, list_b, &g->io.fs->vis_count_b, g->bricks, g->counters.view(g->io.slot, warps),
+                               g->integrate_grid, g->io.dual ? g->io.compute2 : g->io.compute);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
     g->frames++;
@@ -629,6 +682,8 @@ extern "C" int tsdf_grid_download_device(tsdf_grid *g, float *d_tsdf, float *d_w
 {
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
+    int rc = g->io.join();
+    if (rc) return rc;
     launch_unbrick(g->bricks, (int)g->n_x_local, (int)g->geom.dim[1], (int)g->geom.dim[2], g->geom.nb[1],
                    g->geom.nb[2], d_tsdf, d_weight, d_color, g->sm_count, g->io.compute);
     CUDA_TRY(cudaGetLastError());
@@ -642,6 +697,8 @@ extern "C" int tsdf_grid_download(tsdf_grid *g, float *tsdf, float *weight, floa
     CUDA_TRY(cudaSetDevice(g->device));
     const size_t n = (size_t)g->n_x_local * g->geom.dim[1] * g->geom.dim[2];
     if (!n) return TSDF_OK;
+    int rc = g->io.join();
+    if (rc) return rc;
     // one plane at a time keeps the device-side scratch at 4 B/voxel
     float *scratch = nullptr;
     CUDA_TRY(cudaMalloc(&scratch, n * sizeof(float)));
@@ -669,11 +726,13 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
     CUDA_TRY(cudaSetDevice(g->device));
     const StatsBlock *st = nullptr;
     const int slot = g->frames > 0 ? g->io.slot : 0;
-    int rc = g->counters.collect(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, &st);
+    int rc = g->io.join();
+    if (rc) return rc;
+    rc = g->counters.collect(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, &st);
     if (rc) return rc;
     counters[0] = g->frames > 0 ? (int64_t)st->updated_last : 0;
     counters[1] = (int64_t)st->updated_total;
-    counters[2] = (int64_t)st->last_visited;
+    counters[2] = g->frames > 0 ? (int64_t)st->vis_count : 0;
     counters[3] = g->frames;
     return TSDF_OK;
 }
@@ -685,7 +744,16 @@ extern "C" int tsdf_grid_sync(tsdf_grid *g)
     CUDA_TRY(cudaStreamSynchronize(g->io.copy));
     CUDA_TRY(cudaStreamSynchronize(g->io.pre));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));
+    CUDA_TRY(cudaStreamSynchronize(g->io.compute2));
+    g->io.pending2 = false;
     return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_flush(tsdf_grid *g)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    return g->io.join();
 }
 
 extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)
@@ -698,6 +766,10 @@ extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)
 extern "C" int tsdf_grid_set_profiling(tsdf_grid *g, int on)
 {
     BAD_ARG(!g, "NULL handle");
+    if (g->profile_stages != (on != 0)) { // the integrate kernels change streams: drain both first
+        int rc = tsdf_grid_sync(g);
+        if (rc) return rc;
+    }
     g->profile_stages = on != 0;
     return TSDF_OK;
 }

@@ -69,31 +69,48 @@ __global__ void k_depth_u16(const uint16_t *__restrict__ raw, double *__restrict
     }
 }
 
-// One thread per local brick; visible bricks are appended with one atomic per warp.
+// One thread per local brick; visible bricks are appended with one atomic per warp and list.
+// With `classes` == 2 the bricks are dealt into two lists by the parity of (local bx + by + bz), a
+// 3-D checkerboard: the two lists never share a brick, so their integrate kernels are independent
+// and run on two streams -- the second list's CTAs fill the SM slots that the first kernel's tail
+// leaves idle, and the next frame's first kernel does the same for the second (capi_grid.cu).
 __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, int nbz, int rank, int world,
-                              BrickRef *__restrict__ list, FrameScratch *fs)
+                              int classes, BrickRef *__restrict__ list_a, BrickRef *__restrict__ list_b,
+                              FrameScratch *fs)
 {
     const int n = nlbx * nby * nbz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
-    int bx = 0, by = 0, bz = 0;
+    int bx = 0, by = 0, bz = 0, cls = 0;
     if (i < n) {
         bz = i % nbz;
         by = (i / nbz) % nby;
-        bx = (i / (nbz * nby)) * world + rank;
+        const int lbx = i / (nbz * nby);
+        bx = lbx * world + rank;
+        cls = classes > 1 ? ((lbx + by + bz) & 1) : 0;
         c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
         vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, vis);
     if (!ballot) return;
+    const unsigned in_b = __ballot_sync(0xffffffffu, vis && cls == 1);
+    const unsigned in_a = ballot & ~in_b;
     const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&fs->vis_count, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
+    int base_a = 0, base_b = 0;
+    if (lane == 0) {
+        if (in_a) base_a = atomicAdd(&fs->vis_count, __popc(in_a));
+        if (in_b) base_b = atomicAdd(&fs->vis_count_b, __popc(in_b));
+    }
+    base_a = __shfl_sync(0xffffffffu, base_a, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
     if (vis) {
         BrickRef r;
         r.bx = bx; r.by = by; r.bz = bz; r.storage = (uint32_t)i;
-        list[base + __popc(ballot & ((1u << lane) - 1u))] = r;
+        const unsigned below = (1u << lane) - 1u;
+        if (cls == 1)
+            list_b[base_b + __popc(in_b & below)] = r;
+        else
+            list_a[base_a + __popc(in_a & below)] = r;
     }
 }
 
@@ -112,12 +129,12 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
 #if INTEGRATE_STAGED
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
-k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
-                  FrameScratch *fs, Totals *tot, UpdateCounters uc)
+k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
+                  float *__restrict__ bricks, UpdateCounters uc)
 {
     __shared__ __align__(128) float s_rec[2][BRICK_FLOATS];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const int n = fs->vis_count;
+    const int n = *count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
     if (t == 0) {
@@ -162,7 +179,6 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         uc.frame[w] = my_updates;
         uc.total[w] += my_updates;
     }
-    if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
 
 #else
@@ -170,10 +186,10 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
 // depth pixels are requested (kept for A/B measurements, -DINTEGRATE_STAGED=0).
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
-k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, float *__restrict__ bricks,
-                  FrameScratch *fs, Totals *tot, UpdateCounters uc)
+k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
+                  float *__restrict__ bricks, UpdateCounters uc)
 {
-    const int n = fs->vis_count;
+    const int n = *count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
     unsigned my_updates = 0;
@@ -200,7 +216,6 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         uc.frame[w] = my_updates;
         uc.total[w] += my_updates;
     }
-    if (blockIdx.x == 0 && t == 0) tot->last_visited = (unsigned long long)n;
 }
 #endif
 
@@ -226,7 +241,8 @@ __global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScrat
         StatsBlock r;
         r.updated_last = a; r.updated_total = b;
         r.last_visited = tot->last_visited; r.max_probe = tot->max_probe; r.error = tot->error;
-        r.cand_count = fs ? fs->cand_count : 0; r.new_keys = fs ? fs->new_keys : 0; r.vis_count = fs ? fs->vis_count : 0;
+        r.cand_count = fs ? fs->cand_count : 0; r.new_keys = fs ? fs->new_keys : 0;
+        r.vis_count = fs ? fs->vis_count + fs->vis_count_b : 0;
         r.n_entries = n_entries ? *n_entries : 0; r.heap_top = heap_top ? *heap_top : 0; r.pad = 0;
         *out = r;
     }
@@ -272,11 +288,12 @@ void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale
 }
 
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
-                        BrickRef *list, FrameScratch *fs, cudaStream_t s)
+                        int classes, BrickRef *list_a, BrickRef *list_b, FrameScratch *fs, cudaStream_t s)
 {
     const long long n = (long long)nlbx * nby * nbz;
     if (!n) return;
-    k_cull_bricks<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, list, fs);
+    k_cull_bricks<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, classes, list_a,
+                                                              list_b, fs);
 }
 
 #ifndef INTEGRATE_RESERVE_CTAS
@@ -297,13 +314,13 @@ int integrate_dense_ctas_per_sm()
     return n > 0 ? n : 1;
 }
 
-void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
-                            FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s)
+void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
+                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s)
 {
     if (f.unit_w)
-        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot, uc);
+        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc);
     else
-        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, bricks, fs, tot, uc);
+        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc);
 }
 
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,

@@ -16,7 +16,7 @@ struct FrameScratch {
     int cand_count;              // hash: candidate keys emitted by the ray walk (after dedup)
     int new_keys;                // hash: keys inserted this frame
     int error;                   // sticky per-frame error flag (tsdf_status), 0 = ok
-    int pad;
+    int vis_count_b;             // dense: entries in the second visible-brick list (checkerboard class 1)
 };
 
 // Max valid depth per pixel tile, 4 levels: 8, 16, 32, 64 px tiles (0 = no valid pixel in the tile).
@@ -54,14 +54,14 @@ void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_
 void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
                        const TilePyramid &pyr, int H, int W, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
-                        BrickRef *list, FrameScratch *fs, cudaStream_t s);
+                        int classes, BrickRef *list_a, BrickRef *list_b, FrameScratch *fs, cudaStream_t s);
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
 void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
                           const int *heap_top, StatsBlock *out, cudaStream_t s);
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
-void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, float *bricks,
-                            FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s);
+void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
+                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s);
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
                     float *col, int sm_count, cudaStream_t s);
 

@@ -163,6 +163,11 @@ class TSDFVolume:
     def sync(self):
         _capi.check(self._lib.tsdf_grid_sync(self._handle))
 
+    def flush(self):
+        """Device-side join: the stream of cuda_stream() waits for every kernel issued so far
+        (the host does not block).  Record timing events after this."""
+        _capi.check(self._lib.tsdf_grid_flush(self._handle))
+
     def last_kernel_ms(self):
         ms = C.c_float()
         _capi.check(self._lib.tsdf_grid_last_kernel_ms(self._handle, C.byref(ms)))
