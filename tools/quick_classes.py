@@ -11,8 +11,9 @@ dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), np.linalg.inv(p)
 H, W = frames[0][1].shape
 worlds = [int(a) for a in sys.argv[1:]] or [1, 8]
 for world in worlds:
-    for classes in (1, 2, 1, 2):
+    for classes, ctas in ((1, 14), (2, 14), (3, 14), (4, 14), (2, 16), (2, 12), (4, 16), (2, 14)):
         os.environ["TSDF_DENSE_CLASSES"] = str(classes)
+        os.environ["TSDF_DENSE_CTAS_PER_SM"] = str(ctas)
         vol = grid_fusion.TSDFVolume(room.copy(), 0.01, rank=0, world_size=world)
         stream = torch.cuda.ExternalStream(vol.cuda_stream())
         res = []
@@ -27,6 +28,6 @@ for world in worlds:
             vol.flush(); e1.record(stream); vol.sync()
             res.append((1e3 * e0.elapsed_time(e1) / (4 * nfr), 1e6 * t_issue / (4 * nfr)))
         st = vol.stats()
-        print("world %d classes %d: device us/frame %s | host issue us/frame %.1f | updated_total %d" % (
-            world, classes, " ".join("%.1f" % r[0] for r in res), res[-1][1], st["updated_total"]), flush=True)
+        print("world %d classes %d ctas/SM %d: device us/frame %s | host issue us/frame %.1f | updated_total %d" % (
+            world, classes, ctas, " ".join("%.1f" % r[0] for r in res), res[-1][1], st["updated_total"]), flush=True)
         vol.close()

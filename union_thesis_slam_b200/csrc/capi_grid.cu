@@ -141,7 +141,14 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
 int FrameIO::init()
 {
     CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&compute2, cudaStreamNonBlocking));
+    for (int k = 0; k < MAX_SIDE; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&side_end[k]));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&side_int_done[k][i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&side_slot_free[k][i], cudaEventDisableTiming));
+        }
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     {   // preparation kernels are short and on the critical path of the next frame: highest priority
         int lo = 0, hi = 0;
@@ -153,12 +160,9 @@ int FrameIO::init()
         CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&pre_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&int_done[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&int_done2[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&slot_free2[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreate(&k_begin));
     CUDA_TRY(cudaEventCreate(&k_end));
-    CUDA_TRY(cudaEventCreate(&k_end2));
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&k_mark[i]));
     return TSDF_OK;
 }
@@ -174,7 +178,7 @@ int FrameIO::ensure(int npix)
     if (npix <= cap_pix) return TSDF_OK;
     CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
-    CUDA_TRY(cudaStreamSynchronize(compute2));
+    { int rc_ = sync_side(); if (rc_) return rc_; }
     CUDA_TRY(cudaStreamSynchronize(copy));
     for (int i = 0; i < 2; ++i) {
         if (d_rgb[i]) cudaFree(d_rgb[i]);
@@ -205,7 +209,7 @@ int FrameIO::ensure_tiles(int H, int W)
     if (scratch_slot[0] && H == tiles_H && W == tiles_W) return TSDF_OK;
     CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
-    CUDA_TRY(cudaStreamSynchronize(compute2));
+    { int rc_ = sync_side(); if (rc_) return rc_; }
     size_t off[4], total = 256; // FrameScratch lives in the first 256 bytes
     TilePyramid p{};
     for (int l = 1; l <= 3; ++l) {
@@ -263,7 +267,7 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     }
     // the device slot was last read by the kernels of the frame two calls ago
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
-    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free2[s], 0));
+    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth[s], src_depth, (size_t)npix * sizeof(double), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -294,7 +298,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
         src_depth = reinterpret_cast<const uint16_t *>(h_depth[s]);
     }
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
-    CUDA_TRY(cudaStreamWaitEvent(copy, slot_free2[s], 0));
+    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth16[s], src_depth, (size_t)npix * sizeof(uint16_t), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -316,7 +320,7 @@ int FrameIO::begin_kernels()
     pyr = pyr_slot[slot];
     // the integrate kernel of the frame two calls ago was the last reader of this slot
     CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
-    CUDA_TRY(cudaStreamWaitEvent(pre, int_done2[slot], 0));
+    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
     CUDA_TRY(cudaEventRecord(k_begin, pre));
     CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
@@ -327,16 +331,27 @@ int FrameIO::prepared()
 {
     CUDA_TRY(cudaEventRecord(pre_done[slot], pre));
     CUDA_TRY(cudaStreamWaitEvent(compute, pre_done[slot], 0));
-    if (dual) CUDA_TRY(cudaStreamWaitEvent(compute2, pre_done[slot], 0));
+    for (int k = 0; k < n_side; ++k) CUDA_TRY(cudaStreamWaitEvent(side[k], pre_done[slot], 0));
     return TSDF_OK;
 }
 
 int FrameIO::join()
 {
-    if (!pending2) return TSDF_OK;
-    // int_done2[slot] is the last event recorded on compute2
-    CUDA_TRY(cudaStreamWaitEvent(compute, int_done2[slot], 0));
-    pending2 = false;
+    for (int k = 0; k < MAX_SIDE; ++k) {
+        if (!side_pending[k]) continue;
+        // side_end[k] is the last event recorded on side[k]
+        CUDA_TRY(cudaStreamWaitEvent(compute, side_end[k], 0));
+        side_pending[k] = false;
+    }
+    return TSDF_OK;
+}
+
+int FrameIO::sync_side()
+{
+    for (int k = 0; k < MAX_SIDE; ++k) {
+        if (side[k]) CUDA_TRY(cudaStreamSynchronize(side[k]));
+        side_pending[k] = false;
+    }
     return TSDF_OK;
 }
 
@@ -365,16 +380,16 @@ int FrameIO::end_kernels()
 {
     CUDA_TRY(cudaEventRecord(k_end, compute));
     CUDA_TRY(cudaEventRecord(int_done[slot], compute));
-    end2 = dual;
-    if (dual) {
-        CUDA_TRY(cudaEventRecord(k_end2, compute2));
-        CUDA_TRY(cudaEventRecord(int_done2[slot], compute2));
-        pending2 = true;
+    ended_side = n_side;
+    for (int k = 0; k < n_side; ++k) {
+        CUDA_TRY(cudaEventRecord(side_end[k], side[k]));
+        CUDA_TRY(cudaEventRecord(side_int_done[k][slot], side[k]));
+        side_pending[k] = true;
     }
     timed = true;
     if (cur >= 0) {
         CUDA_TRY(cudaEventRecord(slot_free[cur], compute));
-        if (dual) CUDA_TRY(cudaEventRecord(slot_free2[cur], compute2));
+        for (int k = 0; k < n_side; ++k) CUDA_TRY(cudaEventRecord(side_slot_free[k][cur], side[k]));
         cur = -1;
     }
     return TSDF_OK;
@@ -386,10 +401,10 @@ int FrameIO::last_ms(float *ms)
     BAD_ARG(!timed, "no frame integrated yet");
     CUDA_TRY(cudaEventSynchronize(k_end));
     CUDA_TRY(cudaEventElapsedTime(ms, k_begin, k_end));
-    if (end2) { // the frame's second integrate kernel ran on compute2: whichever ended last
+    for (int k = 0; k < ended_side; ++k) { // sibling integrate kernels of the frame: whichever ended last
         float ms2 = 0.f;
-        CUDA_TRY(cudaEventSynchronize(k_end2));
-        CUDA_TRY(cudaEventElapsedTime(&ms2, k_begin, k_end2));
+        CUDA_TRY(cudaEventSynchronize(side_end[k]));
+        CUDA_TRY(cudaEventElapsedTime(&ms2, k_begin, side_end[k]));
         if (ms2 > *ms) *ms = ms2;
     }
     return TSDF_OK;
@@ -399,11 +414,13 @@ void FrameIO::release()
 {
     if (pre) cudaStreamSynchronize(pre);
     if (compute) cudaStreamSynchronize(compute);
-    if (compute2) cudaStreamSynchronize(compute2);
+    sync_side();
     if (copy) cudaStreamSynchronize(copy);
     for (int i = 0; i < 2; ++i) {
-        if (int_done2[i]) cudaEventDestroy(int_done2[i]);
-        if (slot_free2[i]) cudaEventDestroy(slot_free2[i]);
+        for (int k = 0; k < MAX_SIDE; ++k) {
+            if (side_int_done[k][i]) cudaEventDestroy(side_int_done[k][i]);
+            if (side_slot_free[k][i]) cudaEventDestroy(side_slot_free[k][i]);
+        }
         if (cfold_slot[i]) cudaFree(cfold_slot[i]);
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
@@ -420,9 +437,11 @@ void FrameIO::release()
         if (k_mark[i]) cudaEventDestroy(k_mark[i]);
     if (k_begin) cudaEventDestroy(k_begin);
     if (k_end) cudaEventDestroy(k_end);
-    if (k_end2) cudaEventDestroy(k_end2);
     if (compute) cudaStreamDestroy(compute);
-    if (compute2) cudaStreamDestroy(compute2);
+    for (int k = 0; k < MAX_SIDE; ++k) {
+        if (side_end[k]) cudaEventDestroy(side_end[k]);
+        if (side[k]) cudaStreamDestroy(side[k]);
+    }
     if (copy) cudaStreamDestroy(copy);
     if (pre) cudaStreamDestroy(pre);
 }
@@ -490,9 +509,9 @@ struct tsdf_grid {
     int64_t n_x_local = 0;     // local voxel rows
     size_t nbricks = 0;
     float *bricks = nullptr;
-    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity: [class 0 | class 1]
-    int classes = 2;           // independent checkerboard classes of bricks (1 or 2), one integrate kernel each
-    size_t list_b_off = 0;     // where the class-1 list starts inside vis_list[]
+    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity: classes x [class_cap]
+    int classes = 2;           // independent classes of bricks (1..DENSE_MAX_CLASSES), one integrate kernel each
+    size_t class_cap = 0;      // capacity of one class's list inside vis_list[]
     Totals *tot = nullptr;
     int integrate_grid = 0;
     int64_t frames = 0;
@@ -543,8 +562,10 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
         g->n_x_local += std::min<int64_t>(BRICK, dim[0] - x0);
     }
     g->nbricks = (size_t)g->nlbx * g->geom.nb[1] * g->geom.nb[2];
-    if (const char *e = getenv("TSDF_DENSE_CLASSES")) g->classes = atoi(e) == 1 ? 1 : 2;
-    g->list_b_off = (g->nbricks + 1) / 2; // a box's checkerboard has at most ceil(n/2) cells of class 0
+    // measurement knobs (profiles/r1_dense_classes.md); the defaults are the measured best
+    if (const char *e = getenv("TSDF_DENSE_CLASSES")) g->classes = std::min(DENSE_MAX_CLASSES, std::max(1, atoi(e)));
+    // (lbx + by + bz) % classes: every z-column holds at most ceil(nbz / classes) bricks of a class
+    g->class_cap = (size_t)g->nlbx * g->geom.nb[1] * ((g->geom.nb[2] + g->classes - 1) / g->classes);
     if (g->nbricks >= (size_t)1 << 31) {
         grid_free(g);
         tsdf_set_error("too many bricks per rank (%zu)", g->nbricks);
@@ -553,8 +574,8 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     cudaError_t e;
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
     if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list[0], nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list[1], nb_alloc * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list[0], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list[1], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
         cudaGetLastError();
@@ -566,6 +587,7 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     // the persistent integrate grid leaves INTEGRATE_RESERVE_CTAS CTA slots per SM free so that the
     // next frame's preparation kernels (other stream) can run beside it
     g->integrate_grid = sm * std::max(1, integrate_dense_ctas_per_sm() - integrate_reserve_ctas());
+    if (const char *e = getenv("TSDF_DENSE_CTAS_PER_SM")) g->integrate_grid = sm * std::min(32, std::max(1, atoi(e)));
     if ((rc = g->counters.init(g->classes * g->integrate_grid * (INTEGRATE_THREADS / 32)))) {
         grid_free(g);
         return rc;
@@ -596,24 +618,23 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     f.unit_w = g->unit_w ? 1 : 0;
     // preparation (stream `pre`, overlaps the previous frame's integrate kernels)
     launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, g->io.pre);
-    BrickRef *list_b = list + g->list_b_off;
-    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list, list_b,
+    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list, g->class_cap,
                        g->io.fs, g->io.pre);
-    // Two independent classes of bricks, one kernel each on its own stream: kernel B's CTAs take the
-    // SM slots kernel A's tail frees, and the next frame's kernel A does the same for B, so neither
-    // the launch gap nor the drain of the persistent grids leaves the SMs idle.  With stage profiling
-    // on, both run on `compute` so that the stage marks delimit them.
-    g->io.dual = g->classes == 2 && !g->profile_stages;
-    if (!g->io.dual && (rc = g->io.join())) return rc;
+    // Independent classes of bricks, one kernel each on its own stream: the next kernel's CTAs take
+    // the SM slots a kernel's tail frees, and the next frame's first kernel does the same for the
+    // last one, so neither the launch gap nor the drain of the persistent grids leaves the SMs idle.
+    // With stage profiling on, all run on `compute` so that the stage marks delimit them.
+    g->io.n_side = g->profile_stages ? 0 : g->classes - 1;
+    if (!g->io.n_side && (rc = g->io.join())) return rc;
     if ((rc = g->io.prepared())) return rc;
     if (g->profile_stages && (rc = g->io.mark())) return rc;
     const VolumeParams vp = g->geom.params();
     const int warps = g->integrate_grid * (INTEGRATE_THREADS / 32);
-    launch_integrate_dense(f, vp, list, &g->io.fs->vis_count, g->bricks, g->counters.view(g->io.slot), g->integrate_grid,
-                           g->io.compute);
-    if (g->classes == 2)
-        launch_integrate_dense(f, vp, list_b, &g->io.fs->vis_count_b, g->bricks, g->counters.view(g->io.slot, warps),
-                               g->integrate_grid, g->io.dual ? g->io.compute2 : g->io.compute);
+    for (int k = 0; k < g->classes; ++k) {
+        const int *count = k ? &g->io.fs->vis_extra[k - 1] : &g->io.fs->vis_count;
+        launch_integrate_dense(f, vp, list + k * g->class_cap, count, g->bricks, g->counters.view(g->io.slot, k * warps),
+                               g->integrate_grid, (k && g->io.n_side) ? g->io.side[k - 1] : g->io.compute);
+    }
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.end_kernels())) return rc;
     g->frames++;
@@ -744,9 +765,7 @@ extern "C" int tsdf_grid_sync(tsdf_grid *g)
     CUDA_TRY(cudaStreamSynchronize(g->io.copy));
     CUDA_TRY(cudaStreamSynchronize(g->io.pre));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));
-    CUDA_TRY(cudaStreamSynchronize(g->io.compute2));
-    g->io.pending2 = false;
-    return TSDF_OK;
+    return g->io.sync_side();
 }
 
 extern "C" int tsdf_grid_flush(tsdf_grid *g)

@@ -70,13 +70,15 @@ __global__ void k_depth_u16(const uint16_t *__restrict__ raw, double *__restrict
 }
 
 // One thread per local brick; visible bricks are appended with one atomic per warp and list.
-// With `classes` == 2 the bricks are dealt into two lists by the parity of (local bx + by + bz), a
-// 3-D checkerboard: the two lists never share a brick, so their integrate kernels are independent
-// and run on two streams -- the second list's CTAs fill the SM slots that the first kernel's tail
-// leaves idle, and the next frame's first kernel does the same for the second (capi_grid.cu).
+// The bricks are dealt into `classes` lists by (local bx + by + bz) % classes (a 3-D checkerboard
+// for two classes).  The lists never share a brick, so their integrate kernels are independent and
+// run on separate streams: the next list's CTAs fill the SM slots that a kernel's tail leaves idle,
+// and the next frame's first kernel does the same for the last one (capi_grid.cu).
+// Class k's list starts at lists + k * class_cap; its length is counted in fs (dense_count()).
+__device__ __forceinline__ int *dense_count(FrameScratch *fs, int k) { return k ? &fs->vis_extra[k - 1] : &fs->vis_count; }
+
 __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, int nbz, int rank, int world,
-                              int classes, BrickRef *__restrict__ list_a, BrickRef *__restrict__ list_b,
-                              FrameScratch *fs)
+                              int classes, BrickRef *__restrict__ lists, size_t class_cap, FrameScratch *fs)
 {
     const int n = nlbx * nby * nbz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,30 +89,23 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
         by = (i / nbz) % nby;
         const int lbx = i / (nbz * nby);
         bx = lbx * world + rank;
-        cls = classes > 1 ? ((lbx + by + bz) & 1) : 0;
+        cls = (lbx + by + bz) % classes;
         c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
         vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, vis);
-    if (!ballot) return;
-    const unsigned in_b = __ballot_sync(0xffffffffu, vis && cls == 1);
-    const unsigned in_a = ballot & ~in_b;
+    if (!__ballot_sync(0xffffffffu, vis)) return;
     const int lane = threadIdx.x & 31;
-    int base_a = 0, base_b = 0;
-    if (lane == 0) {
-        if (in_a) base_a = atomicAdd(&fs->vis_count, __popc(in_a));
-        if (in_b) base_b = atomicAdd(&fs->vis_count_b, __popc(in_b));
-    }
-    base_a = __shfl_sync(0xffffffffu, base_a, 0);
-    base_b = __shfl_sync(0xffffffffu, base_b, 0);
-    if (vis) {
-        BrickRef r;
-        r.bx = bx; r.by = by; r.bz = bz; r.storage = (uint32_t)i;
-        const unsigned below = (1u << lane) - 1u;
-        if (cls == 1)
-            list_b[base_b + __popc(in_b & below)] = r;
-        else
-            list_a[base_a + __popc(in_a & below)] = r;
+    for (int k = 0; k < classes; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, vis && cls == k);
+        if (!m) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(dense_count(fs, k), __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (vis && cls == k) {
+            BrickRef r;
+            r.bx = bx; r.by = by; r.bz = bz; r.storage = (uint32_t)i;
+            lists[(size_t)k * class_cap + base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
     }
 }
 
@@ -242,7 +237,7 @@ __global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScrat
         r.updated_last = a; r.updated_total = b;
         r.last_visited = tot->last_visited; r.max_probe = tot->max_probe; r.error = tot->error;
         r.cand_count = fs ? fs->cand_count : 0; r.new_keys = fs ? fs->new_keys : 0;
-        r.vis_count = fs ? fs->vis_count + fs->vis_count_b : 0;
+        r.vis_count = fs ? fs->vis_count + fs->vis_extra[0] + fs->vis_extra[1] + fs->vis_extra[2] : 0;
         r.n_entries = n_entries ? *n_entries : 0; r.heap_top = heap_top ? *heap_top : 0; r.pad = 0;
         *out = r;
     }
@@ -288,12 +283,12 @@ void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale
 }
 
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
-                        int classes, BrickRef *list_a, BrickRef *list_b, FrameScratch *fs, cudaStream_t s)
+                        int classes, BrickRef *lists, size_t class_cap, FrameScratch *fs, cudaStream_t s)
 {
     const long long n = (long long)nlbx * nby * nbz;
     if (!n) return;
-    k_cull_bricks<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, classes, list_a,
-                                                              list_b, fs);
+    k_cull_bricks<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f, c, nlbx, nby, nbz, rank, world, classes, lists,
+                                                              class_cap, fs);
 }
 
 #ifndef INTEGRATE_RESERVE_CTAS

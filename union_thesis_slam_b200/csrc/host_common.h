@@ -74,17 +74,19 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
 //    already pinned) on the `copy` stream.
 //  * Per-frame preparation kernels (colour fold, tile pyramid, culling / ray walk, compaction) run
 //    on the `pre` stream, the integrate kernel on `compute` (the dense grid's second, independent
-//    half of the bricks on `compute2`).  All per-frame scratch (folded colour,
+//    classes of bricks on the `side` streams).  All per-frame scratch (folded colour,
 //    FrameScratch, tile pyramid, and the handles' visible lists) is double-buffered by frame
 //    parity, so the preparation of frame n+1 overlaps the integration of frame n.
 struct FrameIO {
     cudaStream_t compute = nullptr, copy = nullptr, pre = nullptr;
-    // second integrate stream of the dense grid (independent checkerboard class, see k_cull_bricks);
-    // `dual` is set by the handle for the frames whose second kernel is issued on it
-    cudaStream_t compute2 = nullptr;
-    bool dual = false;
-    cudaEvent_t int_done2[2] = {nullptr, nullptr}, slot_free2[2] = {nullptr, nullptr};
-    bool pending2 = false; // work issued on compute2 that `compute` has not been made to wait for
+    // sibling integrate streams of the dense grid (independent classes of bricks, see k_cull_bricks);
+    // n_side is set by the handle: how many of them the frame being issued uses (0: all on `compute`)
+    static const int MAX_SIDE = DENSE_MAX_CLASSES - 1;
+    cudaStream_t side[MAX_SIDE] = {};
+    int n_side = 0;
+    cudaEvent_t side_int_done[MAX_SIDE][2] = {}, side_slot_free[MAX_SIDE][2] = {}, side_end[MAX_SIDE] = {};
+    bool side_pending[MAX_SIDE] = {}; // work issued on side[k] that `compute` has not been made to wait for
+    int ended_side = 0;               // side streams used by the last frame issued (for last_ms)
     int cap_pix = 0;
     uint8_t *d_rgb[2] = {nullptr, nullptr};
     double *d_depth[2] = {nullptr, nullptr};
@@ -105,8 +107,7 @@ struct FrameIO {
     int tiles_H = 0, tiles_W = 0;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
     cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr};
-    cudaEvent_t k_begin = nullptr, k_end = nullptr, k_end2 = nullptr; // k_end2: end of the kernel on compute2
-    bool end2 = false;
+    cudaEvent_t k_begin = nullptr, k_end = nullptr;
     cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
     int n_marks = 0;
     int next = 0, cur = -1;
@@ -129,7 +130,8 @@ struct FrameIO {
     int prepared();    // preparation kernels issued: `compute` waits for them
     int end_kernels(); // integrate issued: records timing, frees the scratch and upload slots
     int mark(); // records a stage boundary (up to 3 per frame)
-    int join(); // `compute` waits (on the device) for everything issued on compute2 so far
+    int join(); // `compute` waits (on the device) for everything issued on the side streams so far
+    int sync_side(); // host waits for the side streams
     int last_ms(float *ms);
     int last_stage_ms(float ms[4], int *n); // durations of the stages delimited by mark()
     void release();

@@ -16,8 +16,10 @@ struct FrameScratch {
     int cand_count;              // hash: candidate keys emitted by the ray walk (after dedup)
     int new_keys;                // hash: keys inserted this frame
     int error;                   // sticky per-frame error flag (tsdf_status), 0 = ok
-    int vis_count_b;             // dense: entries in the second visible-brick list (checkerboard class 1)
+    int vis_extra[3];            // dense: entries in the visible-brick lists of brick classes 1..3
+    int pad;
 };
+#define DENSE_MAX_CLASSES 4
 
 // Max valid depth per pixel tile, 4 levels: 8, 16, 32, 64 px tiles (0 = no valid pixel in the tile).
 // Level 0 is written by prep_frame, levels 1..3 by atomicMax from the same kernel (they are
@@ -54,7 +56,7 @@ void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_
 void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
                        const TilePyramid &pyr, int H, int W, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
-                        int classes, BrickRef *list_a, BrickRef *list_b, FrameScratch *fs, cudaStream_t s);
+                        int classes, BrickRef *lists, size_t class_cap, FrameScratch *fs, cudaStream_t s);
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
 void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
                           const int *heap_top, StatsBlock *out, cudaStream_t s);
