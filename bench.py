@@ -214,26 +214,38 @@ def run_b200(args):
     upd = allreduce(float(vol.stats()["updated_total"] - u0), dist.ReduceOp.SUM if world > 1 else None)
     value = upd / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (integrate_dense), measured live per launch ----------
+    # ---- roofline of the dominant kernel (k_integrate_dense) -----------------------------------
+    # Each frame launches it twice (two independent halves of the visible bricks on sibling streams,
+    # so that one launch's tail is filled by the next); in the timed region the launches run back
+    # to back without gaps, so `achieved` divides the algorithmic bytes of the timed frames by the
+    # duration of the timed region itself (which also contains the overlapped prepare/cull kernels:
+    # conservative).  A second pass times the two launches of every frame alone and serialised
+    # (per-frame sync, nothing overlapped) for the per-launch figures.
+    peak, peak_src = peaks()
+    step_bytes = 24.0 * upd + 12.0 * npix * args.steps * world      # every rank reads the whole frame
+    achieved = step_bytes / world / (ms * 1e-3) / 1e9                # per GPU
     vol.set_profiling(True)
-    k_ms, k_bytes, k_upd = 0.0, 0.0, 0
+    k_ms, k_bytes = 0.0, 0.0
     for i in range(args.steps):
         step(args.warmup + i)
         st = vol.last_stage_ms()
         u = vol.stats()["updated_last"]
         k_ms += st[-1]
-        k_upd += u
         k_bytes += 24.0 * u + 12.0 * npix
     vol.set_profiling(False)
-    peak, peak_src = peaks()
-    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    serial = k_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_integrate_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": k_bytes / args.steps,
+                "definition": "algorithmic bytes of the timed frames / duration of the timed region, per GPU "
+                              "(the kernel's launches run back to back; overlapped prepare/cull time included)",
+                "launches_per_frame": 2,
+                "algorithmic_bytes_per_launch": step_bytes / world / args.steps / 2,
                 "bytes_model": "24 B x voxels updated + 12 B x pixels (SURVEY 8d)",
-                "kernel_ms_per_launch": k_ms / args.steps, "traffic": None,
-                # same bytes over the whole timed step (prepare + cull + integrate), single GPU only
-                "frac_whole_step": (k_bytes / (ms * 1e-3) / 1e9) / peak if world == 1 else None}
+                "serialised": {"achieved": serial, "frac": serial / peak,
+                               "kernel_ms_per_frame": k_ms / args.steps,
+                               "note": "the frame's two launches alone on one stream with a sync per frame: "
+                                       "launch gap and both tails exposed"},
+                "traffic": None}
     traffic_file = os.path.join(ROOT, "profiles", "dense_traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:

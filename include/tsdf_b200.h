@@ -171,6 +171,42 @@ int tsdf_mesh_extract(const float *d_tsdf, const float *d_color, const int64_t d
 int tsdf_mesh_download(tsdf_mesh *m, float *verts, int32_t *faces, float *norms, uint8_t *colors);
 int tsdf_mesh_destroy(tsdf_mesh *m);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-voxel hash CONTAINER with the reference's slot layout.
+ * Replaces the container methods of hash_fusion.HashTable: hash_function (hash_fusion.py:182-190),
+ * add_hash_entry / _add_to_linked_list / _find_next_free_space_and_add_entry (:199-276),
+ * get_hash_entry (:285-320), remove_hash_entry (:331-393), needs_resize / double_table_size
+ * (:156-161, :414-437), the occupancy metrics (:147-180) and the per-voxel integrate loop
+ * (:135-145 with data_structures/voxel.py:19-49).  Buckets of `bucket_size` slots (reference: 5,
+ * last slot = head of the bucket's collision chain), chains as (bucket, slot) offsets, tables in
+ * HBM.  Mutating operations are order-dependent in the reference (the slot an entry lands in
+ * depends on every earlier insert), so vbt_apply executes a batch strictly in order on the device
+ * and returns the reference's own return values; vbt_lookup is a parallel read-only batch.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct tsdf_buckets tsdf_buckets;
+enum { VBT_OP_ADD = 0, VBT_OP_GET = 1, VBT_OP_REMOVE = 2, VBT_OP_INTEGRATE = 3 };
+
+int vbt_create(int64_t n_buckets, int bucket_size, double load_factor, int device, tsdf_buckets **out);
+int vbt_destroy(tsdf_buckets *h);
+/* ops[n] (VBT_OP_*), positions[n][3] voxel coordinates, args[n][5] (may be NULL) =
+ * {dist, folded colour} for INTEGRATE, {.., .., sdf, colour, weight} voxel payload for ADD.
+ * out[n][2]: ADD / GET / INTEGRATE -> (bucket, slot) where the entry is stored / was found, or
+ * (-1, -1); REMOVE -> (1 removed / 0 not found, -1).  An ADD that finds the table at its load
+ * factor doubles it first, like add_hash_entry. */
+int vbt_apply(tsdf_buckets *h, const int32_t *ops, const int64_t *positions, const double *args, int64_t n,
+              int64_t *out);
+/* get_hash_entry for a batch, one device thread per query: out[n][2] = (bucket, slot) or (-1, -1);
+ * voxels (may be NULL) [n][3] = (sdf, colour, weight) of the entries found. */
+int vbt_lookup(tsdf_buckets *h, const int64_t *positions, int64_t n, int64_t *out, double *voxels);
+int vbt_double_table_size(tsdf_buckets *h);
+/* stats[0] buckets (table size), [1] non-empty buckets, [2] entries stored, [3] buckets holding
+ * more than one entry (get_num_collisions), [4] resizes so far, [5] bucket size. */
+int vbt_stats(tsdf_buckets *h, int64_t stats[6]);
+/* Slot layout in (bucket, slot) order.  rows == NULL: only *count.  rows[count][7] =
+ * {bucket, slot, x, y, z, offset bucket, offset slot} (-1, -1 = empty offset); voxels (may be
+ * NULL) [count][3] = (sdf, colour, weight), NaN sdf for an entry stored without a voxel. */
+int vbt_dump(tsdf_buckets *h, int64_t capacity, int64_t *count, int64_t *rows, double *voxels);
+
 #ifdef __cplusplus
 }
 #endif

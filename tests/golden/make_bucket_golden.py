@@ -1,0 +1,185 @@
+"""Golden fixtures for the per-voxel hash CONTAINER, from the UNMODIFIED reference.
+
+    python tests/golden/make_bucket_golden.py
+
+Needs /root/reference (build container only).  Runs the reference ``HashTable`` container methods
+(hash_fusion.py:192-440) on (1) the coordinate lists and op patterns of the reference's own
+tests/hash_map_test.py, (2) seeded random add / get / remove streams with collisions, duplicates,
+chain removals and resizes, (3) the per-voxel integrate loop (hash_fusion.py:135-145) on a small
+synthetic stream, and writes tests/golden/bucket_golden.json: for each case the op stream, every
+return value and the final slot layout (and voxel payloads).  Refuses to write a case the Python
+oracle (oracle/bucket_oracle.py) disagrees with.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import bucket_oracle as bo, ref_runner  # noqa: E402
+
+BOUNDS = [[-4.22106438, 3.86798203], [-2.6663104, 2.60146141], [0., 5.76272371]]  # tests/hash_map_test.py:11
+
+# coordinate lists of tests/hash_map_test.py (test_resize_maintain_num_entries, test_add_until_full_size_10, test_add)
+COORDS_RESIZE = [[80, 56, 0], [66, 23, 1], [64, 5, 2], [77, 87, 3], [22, 55, 4], [1, 62, 5], [54, 98, 6],
+                 [17, 35, 7], [42, 86, 8], [75, 84, 9], [72, 56, 10], [68, 94, 11], [31, 18, 12], [97, 83, 13],
+                 [21, 56, 14], [16, 38, 15], [80, 46, 16], [22, 64, 17], [68, 79, 18], [98, 10, 19],
+                 [26, 31, 20], [83, 53, 21], [11, 7, 22], [92, 7, 23], [76, 81, 24], [89, 75, 25], [2, 71, 26],
+                 [82, 10, 27], [77, 58, 28], [57, 0, 29], [80, 25, 30], [43, 92, 31], [15, 26, 32], [33, 93, 33],
+                 [77, 25, 44], [82, 56, 45], [9, 44, 46], [54, 34, 47], [0, 73, 48], [81, 95, 49]]
+COORDS_FULL10 = COORDS_RESIZE[:34] + [[23, 42, 34], [97, 22, 35], [6, 88, 36], [43, 51, 37], [6, 90, 38], [54, 83, 39]]
+COORDS_ADD = [[4, 43, 0], [48, 37, 1], [37, 33, 2], [0, 42, 3], [44, 11, 4], [2, 42, 5], [40, 0, 6],
+              [22, 43, 7], [22, 15, 8], [12, 4, 9], [38, 44, 10], [24, 8, 11], [18, 9, 12], [36, 26, 13],
+              [11, 42, 14], [5, 17, 15], [3, 38, 16], [13, 12, 17], [1, 43, 18], [18, 40, 19], [22, 3, 20],
+              [28, 40, 21], [3, 8, 22], [45, 25, 23], [15, 21, 24], [26, 49, 25], [9, 20, 26], [13, 42, 27],
+              [3, 47, 28], [3, 37, 29], [33, 14, 30], [46, 44, 31], [5, 22, 32], [33, 4, 33], [20, 41, 34],
+              [23, 48, 35], [35, 48, 36], [23, 25, 37], [9, 17, 38], [6, 38, 39]]
+
+
+def ref_layout(ht):
+    out = []
+    for b, bucket in enumerate(ht._hash_table):
+        if bucket is None:
+            continue
+        for e in range(ht._bucket_size):
+            ent = bucket.get_ith_entry(e)
+            if ent is None:
+                continue
+            off = ent.get_offset() or (-1, -1)
+            p = ent.get_position()
+            out.append([b, e, int(p[0]), int(p[1]), int(p[2]), int(off[0]), int(off[1])])
+    return out
+
+
+def ref_find(ht, entry):
+    """(bucket, slot) of a HashEntry object inside the reference table (identity search)."""
+    if entry is None:
+        return [-1, -1]
+    for b, bucket in enumerate(ht._hash_table):
+        if bucket is None:
+            continue
+        for e in range(ht._bucket_size):
+            if bucket.get_ith_entry(e) is entry:
+                return [b, e]
+    raise AssertionError("entry returned by the reference is not in its table")
+
+
+def run_case(hf, he, vx, name, map_size, ops):
+    """ops: list of [op, x, y, z] (+ [dist, color] for OP_INTEGRATE) or ["resize"]."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = hf.HashTable(np.array(BOUNDS), 0.02, map_size, False)
+    orc = bo.OracleBucketTable(map_size)
+    results = []
+    for op in ops:
+        with contextlib.redirect_stdout(io.StringIO()):
+            if op[0] == "resize":
+                ref.double_table_size()
+                orc.double_table_size()
+                r = o = [ref._table_size, -1]
+                o = [orc.S, -1]
+            elif op[0] == bo.OP_ADD:
+                r = [int(v) for v in ref.add_hash_entry(he.HashEntry(list(op[1:4]), None, None))]
+                o = [int(v) for v in orc.add(op[1:4])]
+            elif op[0] == bo.OP_GET:
+                r = ref_find(ref, ref.get_hash_entry(list(op[1:4])))
+                o = [int(v) for v in orc.find(op[1:4])]
+            elif op[0] == bo.OP_REMOVE:
+                r = [int(ref.remove_hash_entry(he.HashEntry(list(op[1:4]), None, None))), -1]
+                o = [int(orc.remove(op[1:4])), -1]
+            elif op[0] == bo.OP_INTEGRATE:
+                # hash_fusion.py:135-145 with the loop's own variables
+                coord = np.array(op[1:4])
+                dist, color = np.float64(op[4]), np.float32(op[5])
+                target = ref.get_hash_entry(coord)
+                if target is None:
+                    voxel = vx.Voxel()
+                    voxel.integrate(dist, color)
+                    r = [int(v) for v in ref.add_hash_entry(he.HashEntry(coord, None, voxel))]
+                else:
+                    target.integrate_voxel(dist, color)
+                    r = ref_find(ref, target)
+                o = [int(v) for v in orc.integrate(op[1:4], op[4], op[5])]
+            else:
+                raise ValueError(op)
+        assert r == o, "%s: op %r: reference %r, oracle %r" % (name, op, r, o)
+        results.append(r)
+    lay = ref_layout(ref)
+    assert lay == [list(t) for t in orc.layout()], "%s: layouts differ" % name
+    stats = {"table_size": int(ref._table_size), "entries": int(ref.count_num_hash_entries()),
+             "non_empty": int(ref.get_num_non_empty_bucket()), "collisions": int(ref.get_num_collisions()),
+             "load_factor": float(ref.get_load_factor())}
+    assert stats["entries"] == orc.count_num_hash_entries() and stats["non_empty"] == orc.nonempty
+    assert stats["collisions"] == orc.get_num_collisions() and stats["table_size"] == orc.S
+    case = {"name": name, "map_size": map_size, "ops": ops, "results": results, "layout": lay, "stats": stats}
+    if any(op[0] == bo.OP_INTEGRATE for op in ops):
+        vox = []
+        for b, e, *_ in lay:
+            v = ref._hash_table[b].get_ith_entry(e).get_voxel()
+            ov = orc.vox[b * orc.B + e]
+            rv = [float(v.get_sdf()), float(v.get_color()), float(v._weight)]
+            assert rv == [float(t) for t in ov], "%s: voxel at (%d,%d): %r vs %r" % (name, b, e, rv, ov)
+            vox.append([x.hex() for x in rv])
+        case["voxels_hex"] = vox
+    return case
+
+
+def main():
+    _, hf = ref_runner.load()
+    from data_structures import hash_entry as he, voxel as vx
+    A, G, R, I = bo.OP_ADD, bo.OP_GET, bo.OP_REMOVE, bo.OP_INTEGRATE
+    cases = []
+    # (1) the reference's own tests
+    ops = [[A] + c for c in COORDS_RESIZE] + [["resize"]] + [[G] + c for c in COORDS_RESIZE]
+    cases.append(run_case(hf, he, vx, "test_resize_maintain_num_entries", 10, ops))
+    cases.append(run_case(hf, he, vx, "test_add_until_full_size_10", 10, [[A] + c for c in COORDS_FULL10]))
+    cases.append(run_case(hf, he, vx, "test_add", 10, [[A] + c for c in COORDS_ADD]))
+    cases.append(run_case(hf, he, vx, "test_remove_all_entries_full_size_10", 10,
+                          [[A] + c for c in COORDS_ADD] + [[R] + c for c in COORDS_ADD]))
+    cases.append(run_case(hf, he, vx, "test_add_same_hash_value_400", 100, [[A, 0, 0, 0]] * 400))
+    rng = np.random.default_rng(7)
+    ops = [[A, int(rng.integers(500)), int(rng.integers(500)), i] for i in range(450)]
+    cases.append(run_case(hf, he, vx, "test_add_until_full_size_100", 100, ops))
+    # test_general at 1/20 scale: add 4n, remove 2n at random, look the rest up, add 2n more
+    n = 500
+    coords = [[int(rng.integers(500)), int(rng.integers(500)), i] for i in range(4 * n)]
+    ops = [[A] + c for c in coords]
+    left = list(coords)
+    for _ in range(2 * n):
+        c = left.pop(int(rng.integers(len(left) - 1)))
+        ops.append([R] + c)
+    ops += [[G] + c for c in left]
+    ops += [[A, int(rng.integers(500)), int(rng.integers(500)) + 501, i] for i in range(2 * n)]
+    cases.append(run_case(hf, he, vx, "test_general_n500", n, ops))
+    # (2) seeded random streams on small tables: heavy collisions, duplicates, misses, chain removals
+    for seed, size, nops, span in ((11, 7, 300, 6), (12, 16, 600, 9), (13, 64, 1500, 14), (14, 5, 200, 4)):
+        rng = np.random.default_rng(seed)
+        ops = []
+        for _ in range(nops):
+            c = [int(v) for v in rng.integers(-span, span, 3)]
+            ops.append([int(rng.choice([A, A, A, G, R, R])),] + c)
+        cases.append(run_case(hf, he, vx, "random_seed%d_size%d" % (seed, size), size, ops))
+    # (3) the per-voxel integrate loop on a synthetic stream (positions revisited, colours blended)
+    rng = np.random.default_rng(21)
+    ops = []
+    for _ in range(900):
+        c = [int(v) for v in rng.integers(0, 7, 3)]
+        dist = float(np.minimum(1.0, rng.uniform(-1.0, 1.6)))
+        color = float(int(rng.integers(0, 256)) * 65536 + int(rng.integers(0, 256)) * 256 + int(rng.integers(0, 256)))
+        ops.append([I] + c + [dist, color])
+    cases.append(run_case(hf, he, vx, "integrate_loop_seed21", 40, ops))
+    out = os.path.join(HERE, "bucket_golden.json")
+    with open(out, "w") as fh:
+        json.dump({"generated_with": "reference hash_fusion.HashTable container methods (unmodified)",
+                   "bounds": BOUNDS, "cases": cases}, fh, separators=(",", ":"))
+    print("wrote %s: %d cases, %d ops, %.0f kB" % (out, len(cases), sum(len(c["ops"]) for c in cases),
+                                                   os.path.getsize(out) / 1e3))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,216 @@
+"""Device-resident per-voxel container (csrc/bucket_kernels.cu, vbt_* C ABI) -- GPU parity tests.
+
+Shaped like the reference's tests/hash_map_test.py (same bounds literal, coordinate lists, op
+patterns and assertions, driven through the drop-in ``HashTable``), plus replays of the fixtures
+recorded from the unmodified reference container (tests/golden/bucket_golden.json): every return
+value and the final slot layout -- buckets, slots, chain offsets -- must match, and the float64
+voxel payloads of the per-voxel integrate loop must be bit-identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bucket_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "bucket_golden.json")) as fh:
+    GOLD = json.load(fh)
+BOUNDS = GOLD["bounds"]
+
+
+def _table(map_size):
+    from union_thesis_slam_b200 import hash_fusion
+    return hash_fusion.HashTable(np.array(BOUNDS), 0.02, map_size, False)
+
+
+def _replay(vt, case):
+    """Feeds the case's op stream to the device in maximal batches (resizes split them)."""
+    res, batch = [], []
+
+    def flush():
+        if not batch:
+            return
+        ops = np.array([b[0] for b in batch], np.int32)
+        pos = np.array([b[1:4] for b in batch], np.int64)
+        args = np.zeros((len(batch), 5))
+        args[:, 2] = np.nan
+        for i, b in enumerate(batch):
+            if b[0] == bo.OP_INTEGRATE:
+                args[i, 0], args[i, 1] = b[4], b[5]
+        out = vt.apply(ops, pos, args)
+        res.extend([int(r[0]), int(r[1])] for r in out)
+        batch.clear()
+
+    for op in case["ops"]:
+        if op[0] == "resize":
+            flush()
+            vt.double_table_size()
+            res.append([vt.stats()["table_size"], -1])
+        else:
+            batch.append(op)
+    flush()
+    return res
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_device_container_replays_reference(case):
+    from union_thesis_slam_b200 import bucket_table
+    vt = bucket_table.VoxelBucketTable(case["map_size"])
+    assert _replay(vt, case) == case["results"]
+    rows, vox = vt.layout(with_voxels=True)
+    assert rows.tolist() == case["layout"]
+    st, ref = vt.stats(), case["stats"]
+    assert (st["table_size"], st["entries"], st["non_empty_buckets"], st["collisions"]) == (
+        ref["table_size"], ref["entries"], ref["non_empty"], ref["collisions"])
+    assert vt.get_load_factor() == ref["load_factor"]
+    if "voxels_hex" in case:
+        assert [[float(x).hex() for x in v] for v in vox] == case["voxels_hex"]
+    vt.close()
+
+
+def test_one_op_at_a_time_equals_batch():
+    """The reference API is one call per entry; it must land entries exactly where a batch does."""
+    from union_thesis_slam_b200 import bucket_table
+    case = next(c for c in GOLD["cases"] if c["name"] == "random_seed12_size16")
+    vt = bucket_table.VoxelBucketTable(case["map_size"])
+    res = []
+    for op in case["ops"]:
+        e = bucket_table.HashEntry(op[1:4], None, None)
+        if op[0] == bo.OP_ADD:
+            res.append(list(vt.add_hash_entry(e)))
+        elif op[0] == bo.OP_GET:
+            got = vt.get_hash_entry(op[1:4])
+            res.append([-1, -1] if got is None else list(got.slot))
+        else:
+            res.append([vt.remove_hash_entry(e), -1])
+    assert res == case["results"]
+    assert vt.layout().tolist() == case["layout"]
+    vt.close()
+
+
+# ---- the reference's tests/hash_map_test.py, through the drop-in HashTable --------------------
+def _coords(name):
+    case = next(c for c in GOLD["cases"] if c["name"] == name)
+    return [op[1:4] for op in case["ops"] if op[0] == bo.OP_ADD]
+
+
+def test_resize_maintain_num_entries():
+    from union_thesis_slam_b200.bucket_table import HashEntry
+    hash_table = _table(10)
+    world_coords = _coords("test_resize_maintain_num_entries")
+    for position in world_coords:
+        hash_table.add_hash_entry(HashEntry(position, None, None))
+    hash_table.double_table_size()
+    assert hash_table.count_num_hash_entries() == 40
+    for position in world_coords:
+        assert hash_table.get_hash_entry(position) is not None
+    hash_table.close()
+
+
+def test_add_until_full_size_10():
+    from union_thesis_slam_b200.bucket_table import HashEntry
+    hash_table = _table(10)
+    for position in _coords("test_add_until_full_size_10"):
+        hash_table.hash_function(position)
+        hash_table.add_hash_entry(HashEntry(position, None, None))
+    assert hash_table.count_num_hash_entries() == 40
+    hash_table.close()
+
+
+def test_remove_all_entries_full_size_10():
+    from union_thesis_slam_b200.bucket_table import HashEntry
+    hash_table = _table(10)
+    world_coords = _coords("test_add")
+    for position in world_coords:
+        hash_table.add_hash_entry(HashEntry(position, None, None))
+    assert hash_table.count_num_hash_entries() == 40
+    for position in world_coords:
+        hash_table.remove_hash_entry(HashEntry(position, None, None))
+    assert hash_table.get_num_non_empty_buckets() == 0
+    assert hash_table.count_num_hash_entries() == 0
+    hash_table.close()
+
+
+def test_add_until_full_size_1000():
+    hash_map = _table(1000)
+    rng = np.random.default_rng(0)
+    pos = np.stack([rng.integers(0, 500, 4500), rng.integers(0, 500, 4500), np.arange(4500)], 1)
+    hash_map.voxel_table.add_positions(pos)
+    assert hash_map.count_num_hash_entries() == 4500
+    hash_map.close()
+
+
+def test_add_same_hash_value():
+    hash_map = _table(1000)
+    slots = hash_map.voxel_table.add_positions(np.zeros((4000, 3), np.int64))
+    assert hash_map.count_num_hash_entries() == 4000          # identical entries are all stored
+    assert len({tuple(s) for s in slots.tolist()}) == 4000     # each in its own slot
+    orc = bo.OracleBucketTable(1000)
+    assert [list(orc.add([0, 0, 0])) for _ in range(4000)] == slots.tolist()
+    hash_map.close()
+
+
+def test_general():
+    """hash_map_test.py:89-121 at full size (40 000 adds, 20 000 removals, look-ups, 20 000 adds),
+    checked against the oracle op by op."""
+    n = 10000
+    hash_table = _table(n)
+    vt = hash_table.voxel_table
+    rng = np.random.default_rng(1)
+    coords = np.stack([rng.integers(0, 500, 4 * n), rng.integers(0, 500, 4 * n), np.arange(4 * n)], 1)
+    orc = bo.OracleBucketTable(n)
+    assert vt.add_positions(coords).tolist() == [list(orc.add(c)) for c in coords]
+    assert hash_table.count_num_hash_entries() == 4 * n
+    drop = rng.permutation(4 * n)[:2 * n]
+    out = vt.apply(np.full(2 * n, bo.OP_REMOVE, np.int32), coords[drop])
+    assert out[:, 0].tolist() == [orc.remove(c) for c in coords[drop]] and out[:, 0].sum() == 2 * n
+    assert hash_table.count_num_hash_entries() == 2 * n
+    keep = np.setdiff1d(np.arange(4 * n), drop)
+    found = vt.lookup(coords[keep])
+    assert (found[:, 0] >= 0).all() and found.tolist() == [list(orc.find(c)) for c in coords[keep]]
+    assert (vt.lookup(coords[drop])[:, 0] == -1).all()
+    more = np.stack([rng.integers(0, 500, 2 * n), rng.integers(0, 500, 2 * n) + 501, np.arange(2 * n)], 1)
+    assert vt.add_positions(more).tolist() == [list(orc.add(c)) for c in more]
+    assert hash_table.count_num_hash_entries() == 4 * n
+    assert vt.layout().tolist() == [list(r) for r in orc.layout()]
+    st = vt.stats()
+    assert (st["table_size"], st["non_empty_buckets"], st["collisions"]) == (orc.S, orc.nonempty, orc.get_num_collisions())
+    hash_table.close()
+
+
+def test_integrate_voxels_matches_oracle_running_mean():
+    """Per-voxel loop of hash_fusion.py:135-145 + voxel.py:19-49 on a random stream with resizes."""
+    from union_thesis_slam_b200 import bucket_table
+    rng = np.random.default_rng(5)
+    n = 6000
+    pos = rng.integers(0, 12, (n, 3))
+    dist = np.minimum(1.0, rng.uniform(-1.0, 1.5, n))
+    col = (rng.integers(0, 256, n) * 65536 + rng.integers(0, 256, n) * 256 + rng.integers(0, 256, n)).astype(np.float64)
+    vt = bucket_table.VoxelBucketTable(64)
+    orc = bo.OracleBucketTable(64)
+    got = vt.integrate_voxels(pos, dist, col)
+    assert got.tolist() == [list(orc.integrate(p, d, c)) for p, d, c in zip(pos, dist, col)]
+    rows, vox = vt.layout(with_voxels=True)
+    assert rows.tolist() == [list(r) for r in orc.layout()]
+    want = np.array([orc.vox[r[0] * orc.B + r[1]] for r in rows])
+    assert np.array_equal(vox, want)
+    assert vt.stats()["resizes"] == orc.resizes and orc.resizes >= 2
+    v = vt.get_voxel(pos[0])
+    assert (v.get_sdf(), v.get_color(), v.get_weight()) == tuple(orc.get_voxel(pos[0]))
+    vt.close()
+
+
+def test_bad_arguments_raise():
+    from union_thesis_slam_b200 import _capi, bucket_table
+    with pytest.raises(_capi.TSDFError):
+        bucket_table.VoxelBucketTable(0)
+    vt = bucket_table.VoxelBucketTable(8)
+    with pytest.raises(_capi.TSDFError):
+        vt.apply([7], [[0, 0, 0]])
+    with pytest.raises(_capi.TSDFError):
+        vt.apply([bo.OP_ADD], [[1 << 40, 0, 0]])
+    assert vt.get_hash_entry([1, 2, 3]) is None and vt.remove_hash_entry(bucket_table.HashEntry([1, 2, 3], None, None)) == 0
+    vt.close()

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "tsdf_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:tsdf|vh)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:tsdf|vh|vbt)_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")

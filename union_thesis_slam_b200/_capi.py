@@ -50,6 +50,13 @@ SYMBOLS = [
     ("vh_remove_blocks", _i, [_p, _p, _i64, _p]),
     ("vh_sync", _i, [_p]),
     ("vh_last_kernel_ms", _i, [_p, _p]),
+    ("vbt_create", _i, [_i64, _i, _d, _i, _pp]),
+    ("vbt_destroy", _i, [_p]),
+    ("vbt_apply", _i, [_p, _p, _p, _p, _i64, _p]),
+    ("vbt_lookup", _i, [_p, _p, _i64, _p, _p]),
+    ("vbt_double_table_size", _i, [_p]),
+    ("vbt_stats", _i, [_p, _p]),
+    ("vbt_dump", _i, [_p, _i64, _p, _p, _p]),
     ("tsdf_mesh_extract", _i, [_p, _p, _p, _d, _p, _i, _pp, _p, _p]),
     ("tsdf_mesh_download", _i, [_p, _p, _p, _p, _p]),
     ("tsdf_mesh_destroy", _i, [_p]),

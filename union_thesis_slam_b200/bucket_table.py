@@ -1,0 +1,229 @@
+"""Per-voxel hash container with the reference's slot layout, resident on the device.
+
+Mirrors the container half of the reference ``HashTable`` (hash_fusion.py:147-180, 192-440) and
+its value types ``HashEntry`` (data_structures/hash_entry.py) and ``Voxel``
+(data_structures/voxel.py): buckets of five slots, the last one heading the bucket's collision
+chain, chains threaded through ``(bucket, slot)`` offsets into other buckets' free slots,
+resize by re-insertion at 0.75 non-empty buckets.  The tables live in HBM and every operation
+runs in csrc/bucket_kernels.cu behind the ``vbt_*`` C ABI; mutating operations execute strictly
+in call order on the device because the reference's layout is order-dependent (where an entry
+lands depends on everything inserted before it).  Return values -- the ``(bucket, slot)`` pairs
+of ``add_hash_entry``, ``1`` / ``0`` of ``remove_hash_entry`` -- are the reference's.
+
+``get_hash_entry`` returns a snapshot (position, offset, voxel) of the stored entry, not a live
+object: mutate through the table (``integrate_voxels``, ``remove``), not through the snapshot.
+There is no CPU fallback: without the CUDA library and a device the constructor raises.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+
+OP_ADD, OP_GET, OP_REMOVE, OP_INTEGRATE = 0, 1, 2, 3
+P1 = 73856093
+P2 = 19349669
+P3 = 83492791
+
+
+class Voxel:
+    """Value object of data_structures/voxel.py:6-17 (sdf = 1, colour = 0, weight = 0)."""
+
+    def __init__(self, sdf=1, color=0, weight=0):
+        self._sdf = sdf
+        self._color = color
+        self._weight = weight
+
+    def get_sdf(self):
+        return self._sdf
+
+    def get_color(self):
+        return self._color
+
+    def get_weight(self):
+        return self._weight
+
+
+class HashEntry:
+    """Value object of data_structures/hash_entry.py:6-45: (position, offset, voxel)."""
+
+    def __init__(self, position, offset, voxel):
+        self._position = position
+        self._offset = offset
+        self._voxel = voxel
+
+    def get_position(self):
+        return self._position
+
+    def get_voxel(self):
+        return self._voxel
+
+    def set_offset(self, pointer):
+        self._offset = pointer
+
+    def get_offset(self):
+        return self._offset
+
+    def is_empty_offset(self):
+        return self._offset is None
+
+    def equals(self, hash_entry):
+        return np.array_equal(self._position, hash_entry.get_position())
+
+    def match_position(self, position):
+        return np.array_equal(self._position, position)
+
+
+def _payload(voxel):
+    """(sdf, colour, weight) float64 of a Voxel; NaN sdf marks an entry stored without one."""
+    if voxel is None:
+        return (math.nan, 0.0, 0.0)
+    f = [voxel.get_sdf(), voxel.get_color(), voxel.get_weight()]
+    return tuple(math.nan if v is None else float(v) for v in f)
+
+
+class VoxelBucketTable:
+    def __init__(self, map_size=1000000, bucket_size=5, load_factor=0.75, device=0):
+        self._lib = _capi.lib()
+        self._handle = C.c_void_p()
+        self._bucket_size = int(bucket_size)
+        self._load_factor = 0.75 if load_factor is None else float(load_factor)
+        _capi.check(self._lib.vbt_create(int(map_size), self._bucket_size, self._load_factor, int(device),
+                                         C.byref(self._handle)))
+
+    # -- batches ---------------------------------------------------------------------------------
+    def apply(self, ops, positions, args=None):
+        """Executes the operations in order on the device; returns (n, 2) int64 results
+        (see ``vbt_apply`` in include/tsdf_b200.h)."""
+        ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1)
+        pos = np.ascontiguousarray(positions, dtype=np.int64).reshape(-1, 3)
+        if len(ops) != len(pos):
+            raise ValueError("ops and positions differ in length")
+        if args is not None:
+            args = np.ascontiguousarray(args, dtype=np.float64).reshape(len(ops), 5)
+        out = np.full((len(ops), 2), -1, np.int64)
+        _capi.check(self._lib.vbt_apply(self._handle, _capi.ptr(ops), _capi.ptr(pos), _capi.ptr(args), len(ops),
+                                        _capi.ptr(out)))
+        return out
+
+    def lookup(self, positions, with_voxels=False):
+        """Parallel read-only ``get_hash_entry`` of a batch: (n, 2) (bucket, slot) or (-1, -1)."""
+        pos = np.ascontiguousarray(positions, dtype=np.int64).reshape(-1, 3)
+        out = np.full((len(pos), 2), -1, np.int64)
+        vox = np.zeros((len(pos), 3), np.float64) if with_voxels else None
+        _capi.check(self._lib.vbt_lookup(self._handle, _capi.ptr(pos), len(pos), _capi.ptr(out), _capi.ptr(vox)))
+        return (out, vox) if with_voxels else out
+
+    def integrate_voxels(self, positions, dists, colors):
+        """The reference's per-voxel loop (hash_fusion.py:135-145) for a batch of (voxel, dist,
+        folded colour): look up, create + insert on a miss, float64 running mean
+        (data_structures/voxel.py:19-49) either way.  Returns where each voxel is stored."""
+        pos = np.ascontiguousarray(positions, dtype=np.int64).reshape(-1, 3)
+        args = np.zeros((len(pos), 5), np.float64)
+        args[:, 0] = dists
+        args[:, 1] = colors
+        return self.apply(np.full(len(pos), OP_INTEGRATE, np.int32), pos, args)
+
+    # -- reference container methods ---------------------------------------------------------------
+    def hash_function(self, world_coord):
+        """H(x,y,z) = (x*p1 xor y*p2 xor z*p3) mod n (hash_fusion.py:182-190)."""
+        x, y, z = (int(v) for v in world_coord[:3])
+        return ((x * P1) ^ (y * P2) ^ (z * P3)) % self.stats()["table_size"]
+
+    def add_hash_entry(self, hash_entry):
+        """Returns (ith_bucket, ith_entry) where the entry is stored, (-1, -1) if that failed
+        (hash_fusion.py:199-224)."""
+        if hash_entry is None:
+            return -1, -1
+        args = np.zeros((1, 5), np.float64)
+        args[0, 2:] = _payload(hash_entry.get_voxel())
+        r = self.apply([OP_ADD], [hash_entry.get_position()], args)[0]
+        return int(r[0]), int(r[1])
+
+    def add_voxel(self, voxel, world_coord):
+        self.add_hash_entry(HashEntry(world_coord, None, voxel))
+
+    def add_positions(self, positions, voxels=None):
+        """Batch ``add_hash_entry``: (n, 2) slots, in order."""
+        pos = np.ascontiguousarray(positions, dtype=np.int64).reshape(-1, 3)
+        args = np.zeros((len(pos), 5), np.float64)
+        args[:, 2] = math.nan
+        if voxels is not None:
+            args[:, 2:] = [_payload(v) for v in voxels]
+        return self.apply(np.full(len(pos), OP_ADD, np.int32), pos, args)
+
+    def get_hash_entry(self, world_coord):
+        """Snapshot of the stored entry or None (hash_fusion.py:285-310)."""
+        slots, vox = self.lookup([world_coord], with_voxels=True)
+        b, e = int(slots[0, 0]), int(slots[0, 1])
+        if b < 0:
+            return None
+        voxel = None if math.isnan(vox[0, 0]) else Voxel(vox[0, 0], vox[0, 1], vox[0, 2])
+        entry = HashEntry(tuple(int(v) for v in world_coord[:3]), None, voxel)
+        entry.slot = (b, e)
+        return entry
+
+    def get_voxel(self, world_coord):
+        return self.get_hash_entry(world_coord).get_voxel()
+
+    def remove_hash_entry(self, hash_entry):
+        """1 if removed, 0 if not found (hash_fusion.py:331-384)."""
+        return int(self.apply([OP_REMOVE], [hash_entry.get_position()])[0, 0])
+
+    def remove(self, world_coord):
+        self.remove_hash_entry(HashEntry(world_coord, None, None))
+
+    def double_table_size(self):
+        before = self.stats()["table_size"]
+        print("Resizing hash table from {} to {}".format(before, before * 2))
+        _capi.check(self._lib.vbt_double_table_size(self._handle))
+        print("Resize finished.")
+
+    # -- occupancy metrics (hash_fusion.py:147-180) ---------------------------------------------------
+    def stats(self):
+        s = np.zeros(6, np.int64)
+        _capi.check(self._lib.vbt_stats(self._handle, _capi.ptr(s)))
+        names = ["table_size", "non_empty_buckets", "entries", "collisions", "resizes", "bucket_size"]
+        return {k: int(v) for k, v in zip(names, s)}
+
+    def count_num_hash_entries(self):
+        return self.stats()["entries"]
+
+    def get_num_non_empty_bucket(self):
+        return self.stats()["non_empty_buckets"]
+
+    get_num_non_empty_buckets = get_num_non_empty_bucket
+
+    def get_load_factor(self):
+        s = self.stats()
+        return s["non_empty_buckets"] / s["table_size"]
+
+    def needs_resize(self):
+        return self.get_load_factor() >= self._load_factor
+
+    def get_num_collisions(self):
+        return self.stats()["collisions"]
+
+    # -- read-out --------------------------------------------------------------------------------
+    def layout(self, with_voxels=False):
+        """(n, 7) int64 rows {bucket, slot, x, y, z, offset bucket, offset slot} in slot order
+        (offset -1, -1 = empty) and optionally the (n, 3) voxel payloads."""
+        n = C.c_int64()
+        _capi.check(self._lib.vbt_dump(self._handle, 0, C.byref(n), None, None))
+        rows = np.zeros((n.value, 7), np.int64)
+        vox = np.zeros((n.value, 3), np.float64) if with_voxels else None
+        if n.value:
+            _capi.check(self._lib.vbt_dump(self._handle, n.value, C.byref(n), _capi.ptr(rows), _capi.ptr(vox)))
+        return (rows, vox) if with_voxels else rows
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle:
+            self._lib.vbt_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

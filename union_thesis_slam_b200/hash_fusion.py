@@ -64,6 +64,8 @@ class HashTable:
             _capi.ptr(dim), _capi.ptr(self._vol_origin), float(self._voxel_size), float(self._trunc_margin),
             int(map_size), int(heap_blocks), self.device, self.rank, self.world_size, C.byref(self._handle)))
         self._table_size = self.stats()["table_slots"]
+        self._map_size = int(map_size)
+        self._voxels = None  # per-voxel container with the reference's bucket layout, created on first use
 
     # -- hot path ------------------------------------------------------------------------------
     def integrate(self, color_im, depth_im, cam_intr, cam_pose, obs_weight=1.):
@@ -139,6 +141,43 @@ class HashTable:
         _capi.check(self._lib.vh_remove_blocks(self._handle, _capi.ptr(keys), len(keys), C.byref(removed)))
         return removed.value
 
+    # -- per-voxel container API (reference hash_fusion.py:192-440) --------------------------------
+    # The reference keeps one entry per voxel in 5-slot buckets with offset chains and exposes that
+    # container directly (its tests/hash_map_test.py drives it).  Here integrate() stores 8^3 blocks
+    # in the lock-free block table; the reference-layout container is a second device structure
+    # (bucket_table.VoxelBucketTable, csrc/bucket_kernels.cu) of `map_size` buckets that these
+    # calls operate on.  Once it has been used, the occupancy metrics below describe it.
+    @property
+    def voxel_table(self):
+        if self._voxels is None:
+            from . import bucket_table
+            self._voxels = bucket_table.VoxelBucketTable(self._map_size, 5, self._load_factor, self.device)
+        return self._voxels
+
+    def add_voxel(self, voxel, world_coord):
+        self.voxel_table.add_voxel(voxel, world_coord)
+
+    def add_hash_entry(self, hash_entry):
+        return self.voxel_table.add_hash_entry(hash_entry)
+
+    def get_voxel(self, world_coord):
+        return self.voxel_table.get_voxel(world_coord)
+
+    def get_hash_entry(self, world_coord):
+        return self.voxel_table.get_hash_entry(world_coord)
+
+    def remove(self, world_coord):
+        self.voxel_table.remove(world_coord)
+
+    def remove_hash_entry(self, hash_entry):
+        return self.voxel_table.remove_hash_entry(hash_entry)
+
+    def double_table_size(self):
+        self.voxel_table.double_table_size()
+
+    def get_num_collisions(self):
+        return self.voxel_table.get_num_collisions()
+
     # -- occupancy metrics (reference hash_fusion.py:147-180) ------------------------------------
     def stats(self):
         s = np.zeros(12, np.int64)
@@ -149,15 +188,22 @@ class HashTable:
         return {k: int(v) for k, v in zip(names, s)}
 
     def count_num_hash_entries(self):
-        """Number of stored entries; here an entry is an allocated 8^3 block."""
+        """Number of stored entries: voxel entries of the per-voxel container once that is in use,
+        else allocated 8^3 blocks."""
+        if self._voxels is not None:
+            return self._voxels.count_num_hash_entries()
         return self.stats()["blocks"]
 
     def get_num_non_empty_bucket(self):
+        if self._voxels is not None:
+            return self._voxels.get_num_non_empty_bucket()
         return self.stats()["table_keys"]
 
     get_num_non_empty_buckets = get_num_non_empty_bucket
 
     def get_load_factor(self):
+        if self._voxels is not None:
+            return self._voxels.get_load_factor()
         s = self.stats()
         return s["table_keys"] / s["table_slots"]
 
@@ -165,7 +211,10 @@ class HashTable:
         return self.get_load_factor() >= self._load_factor
 
     def hash_function(self, world_coord):
-        """H(x,y,z) = (x*p1 xor y*p2 xor z*p3) mod n (reference hash_fusion.py:182-190)."""
+        """H(x,y,z) = (x*p1 xor y*p2 xor z*p3) mod n (reference hash_fusion.py:182-190); n is the
+        bucket count of the per-voxel container once that is in use, else the block table's slots."""
+        if self._voxels is not None:
+            return self._voxels.hash_function(world_coord)
         x, y, z = (int(v) for v in world_coord[:3])
         return ((x * P1) ^ (y * P2) ^ (z * P3)) % self._table_size
 
@@ -202,6 +251,9 @@ class HashTable:
         return meshing.point_cloud(self)
 
     def close(self):
+        if getattr(self, "_voxels", None) is not None:
+            self._voxels.close()
+            self._voxels = None
         if getattr(self, "_handle", None) is not None and self._handle:
             self._lib.vh_destroy(self._handle)
             self._handle = C.c_void_p()
