@@ -266,3 +266,22 @@ def test_hash_function_matches_reference_kats():
             assert ht.hash_function(k["coord"]) == k["hash"]
     assert ht.hash_function([0, 0, 0]) == 0
     assert ht.get_load_factor() == 0.0 and ht.count_num_hash_entries() == 0
+
+
+def test_allocation_front_ends_agree(monkeypatch):
+    """TSDF_HASH_ALLOC=walk (cone walk per pixel tile, then refine) and =grid (refine tests the
+    bounded super-block grid itself) must allocate the same blocks and produce the same voxels."""
+    from union_thesis_slam_b200 import hash_fusion
+    case = scenes.small_case(seed=77, dims=(70, 45, 52), voxel_size=0.02, hw=(96, 128), nframes=4)
+    out = {}
+    for mode in ("walk", "grid"):
+        monkeypatch.setenv("TSDF_HASH_ALLOC", mode)
+        ht = hash_fusion.HashTable(case["vol_bnds"].copy(), case["voxel_size"], map_size=1 << 14)
+        for c, d, p, obs in case["frames"]:
+            ht.integrate(c, d, case["K"], p, obs_weight=obs)
+        keys, payload = ht.export_blocks()
+        order = np.lexsort(keys.T[::-1])
+        out[mode] = (keys[order], payload[order], ht.stats()["updated_total"])
+        ht.close()
+    assert out["walk"][2] == out["grid"][2] > 0
+    assert np.array_equal(out["walk"][0], out["grid"][0]) and np.array_equal(out["walk"][1], out["grid"][1])

@@ -21,6 +21,12 @@ struct tsdf_hash {
     int64_t frames = 0;
     bool unit_w = true;
     double walk_step_voxels = 16.0; // ray-walk sample spacing: half a super-block
+    // Which super-blocks can the frame touch?  false: K3 tests every super-block of the bounded grid
+    // itself (one warp each, sphere vs frustum + tile depth pyramid; cost scales with the volume).
+    // true: K2's cone walk per pixel tile flags them first (cost scales with pixels x depth).
+    // Both are conservative and K3's per-block test decides, so the allocated set is identical;
+    // TSDF_HASH_ALLOC=walk|grid overrides the default for measurement (profiles/r1_hash_alloc.md).
+    bool ray_walk = false;
 };
 
 static int hash_free(tsdf_hash *h)
@@ -65,6 +71,7 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
             tsdf_set_error("volume has too many blocks along axis %d (limit 32767)", a);
             return TSDF_ERR_BAD_ARG;
         }
+    if (const char *e = getenv("TSDF_HASH_ALLOC")) h->ray_walk = strcmp(e, "walk") == 0;
     int64_t S = 1024;
     while (S < table_slots) S <<= 1;
     h->table_slots = S;
@@ -194,10 +201,12 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     cudaStream_t s = h->io.pre;
     launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->io.fs, h->io.pyr, H, W, s);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
-    launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
-    CUDA_TRY(cudaGetLastError());
-    launch_refine_insert(f, c, h->dev, h->sb_flags, h->io.fs, h->tot, s);
+    if (h->ray_walk) {
+        CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
+        launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
+        CUDA_TRY(cudaGetLastError());
+    }
+    launch_refine_insert(f, c, h->dev, h->ray_walk ? h->sb_flags : nullptr, h->io.fs, h->tot, s);
     CUDA_TRY(cudaGetLastError());
     // a key exists at most once per block of the bounded grid: bound the scan by that, not by the table size
     launch_compact_visible(f, c, h->dev, (int)std::min<int64_t>(h->table_slots, (int64_t)h->dev.nbx * h->dev.nby * h->dev.nbz),

@@ -175,7 +175,9 @@ __global__ void k_walk_coarse(WalkParams w, HashDev h, const float *__restrict__
     if (lane == 0 && my_cand) atomicAdd(&fs->cand_count, my_cand);
 }
 
-// K3: one warp per flagged super-block; each lane tests two of its 64 blocks.  A block whose key
+// K3: one warp per flagged super-block; each lane tests two of its 64 blocks.  Called with
+// sb_flags == nullptr it also decides itself which super-blocks the frame can touch (sphere-vs-
+// frustum + tile-depth-pyramid test of the bounded super-block grid) and K2 is not run at all.  A block whose key
 // is already in the table (presence bitmap) costs one bit test; otherwise the conservative
 // visibility test of the dense grid decides and the key is inserted lock-free (keys only).
 __global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, const uint32_t *__restrict__ sb_flags,
@@ -184,10 +186,13 @@ __global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, const ui
     const int sb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (sb >= h.nsx * h.nsy * h.nsz) return;
-    if (!((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
+    if (sb_flags && !((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
     const int sz = sb % h.nsz, sy = (sb / h.nsz) % h.nsy, sx = sb / (h.nsz * h.nsy);
     c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
     if (!(c.max_depth > 0.0)) return;
+    // grid-scan allocation (no ray walk ran): the conservative visibility test of the whole
+    // super-block stands in for the walk's flag (warp-uniform)
+    if (!sb_flags && !superblock_visible(f, c, sx, sy, sz)) return;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int child = lane * 2 + k;
