@@ -154,6 +154,9 @@ int vh_to_dense_device(tsdf_hash *h, float *d_tsdf, float *d_weight, float *d_co
 int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, int64_t *removed);
 int vh_sync(tsdf_hash *h);
 int vh_last_kernel_ms(tsdf_hash *h, float *ms);
+/* The cudaStream_t the integrate kernel of every frame runs on (it starts after the frame's
+ * allocation / compaction kernels): an event recorded on it after a frame marks that frame's end. */
+int vh_stream(tsdf_hash *h, void **stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Surface extraction for get_mesh / get_point_cloud (grid_fusion.py:322-360,

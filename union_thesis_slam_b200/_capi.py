@@ -50,6 +50,7 @@ SYMBOLS = [
     ("vh_remove_blocks", _i, [_p, _p, _i64, _p]),
     ("vh_sync", _i, [_p]),
     ("vh_last_kernel_ms", _i, [_p, _p]),
+    ("vh_stream", _i, [_p, _pp]),
     ("vbt_create", _i, [_i64, _i, _d, _i, _pp]),
     ("vbt_destroy", _i, [_p]),
     ("vbt_apply", _i, [_p, _p, _p, _p, _i64, _p]),

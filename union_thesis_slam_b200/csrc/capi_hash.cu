@@ -322,6 +322,13 @@ extern "C" int vh_last_kernel_ms(tsdf_hash *h, float *ms)
     return h->io.last_ms(ms);
 }
 
+extern "C" int vh_stream(tsdf_hash *h, void **stream)
+{
+    BAD_ARG(!h || !stream, "NULL argument");
+    *stream = (void *)h->io.compute;
+    return TSDF_OK;
+}
+
 extern "C" int vh_to_dense_device(tsdf_hash *h, float *d_tsdf, float *d_weight, float *d_color)
 {
     BAD_ARG(!h, "NULL handle");

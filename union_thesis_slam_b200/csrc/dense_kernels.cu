@@ -110,11 +110,12 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
 }
 
 // Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
-// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane.
-// Records are double-buffered through shared memory: while brick i is integrated, one thread has
-// already started the 6 KB bulk copy (cp.async.bulk + mbarrier, the TMA path) of brick i+1, so the
-// HBM latency of the record is hidden behind a whole brick of float64 geometry.  Updated voxels
-// are written straight from registers with streaming stores.
+// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane, read with streaming loads right
+// after the depth pixels are requested and written back straight from registers with streaming
+// stores.  One launch per class of bricks (see k_cull_bricks); `count` is that class's list length.
+// -DINTEGRATE_STAGED=1 builds the measured-and-rejected variant instead (profiles/r1_dense_ab.txt):
+// records double-buffered through shared memory by one thread's 6 KB bulk copy (cp.async.bulk +
+// mbarrier, the TMA path) of brick i+1 while brick i is integrated.
 #ifndef INTEGRATE_L2_PREFETCH
 #define INTEGRATE_L2_PREFETCH 0
 #endif
@@ -177,8 +178,6 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
 }
 
 #else
-// Variant without shared-memory staging: records are read with streaming loads right after the
-// depth pixels are requested (kept for A/B measurements, -DINTEGRATE_STAGED=0).
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,

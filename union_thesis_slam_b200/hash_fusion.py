@@ -226,6 +226,12 @@ class HashTable:
         _capi.check(self._lib.vh_last_kernel_ms(self._handle, C.byref(ms)))
         return ms.value
 
+    def cuda_stream(self):
+        """Raw cudaStream_t (int) of the integrate kernels; wrap with torch.cuda.ExternalStream."""
+        s = C.c_void_p()
+        _capi.check(self._lib.vh_stream(self._handle, C.byref(s)))
+        return s.value or 0
+
     def _device_volume(self, dev):
         """(tsdf, color) float32 [X,Y,Z] torch tensors on the device (union over ranks when sharded)."""
         import torch
