@@ -27,6 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
 ROOM = (10.0, 10.0, 4.0)
 VOXEL = 0.01
 IM_W, IM_H = 640, 480
@@ -141,7 +142,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": r["frames_per_s_sample"], "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
     return 0
 
 
@@ -301,7 +302,7 @@ def run_b200(args):
         r = cpu_port(frames, K, room, VOXEL, steps=4, warmup=1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -381,6 +382,18 @@ def bench_hash(args, dev, local, peak, rank=0, world=1):
 
 
 def main():
+    # the drop-in constructors print the reference's banners; keep stdout for the one JSON line
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    try:
+        return _main(real_stdout)
+    finally:
+        sys.stdout = real_stdout
+
+
+def _main(out):
+    global _OUT
+    _OUT = out
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1024)
@@ -414,7 +427,7 @@ def run_hash_only(args):
     line = bench_hash(args, torch.device("cuda", local), local, peaks()[0], rank, world)
     line.update({"higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f64"})
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
