@@ -11,7 +11,7 @@ dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), np.linalg.inv(p)
 H, W = frames[0][1].shape
 worlds = [int(a) for a in sys.argv[1:]] or [1, 8]
 for world in worlds:
-    for classes, ctas in ((1, 14), (2, 14), (3, 14), (4, 14), (2, 16), (2, 12), (4, 16), (2, 14)):
+    for classes, ctas in ((2, 14), (1, 14), (2, 14)):
         os.environ["TSDF_DENSE_CLASSES"] = str(classes)
         os.environ["TSDF_DENSE_CTAS_PER_SM"] = str(ctas)
         vol = grid_fusion.TSDFVolume(room.copy(), 0.01, rank=0, world_size=world)

@@ -144,7 +144,7 @@ int FrameIO::init()
     for (int k = 0; k < MAX_SIDE; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&side_end[k]));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < FRAME_SLOTS; ++i) {
             CUDA_TRY(cudaEventCreateWithFlags(&side_int_done[k][i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&side_slot_free[k][i], cudaEventDisableTiming));
         }
@@ -155,7 +155,7 @@ int FrameIO::init()
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&pre, cudaStreamNonBlocking, hi));
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&pre_done[i], cudaEventDisableTiming));
@@ -180,7 +180,7 @@ int FrameIO::ensure(int npix)
     CUDA_TRY(cudaStreamSynchronize(compute));
     { int rc_ = sync_side(); if (rc_) return rc_; }
     CUDA_TRY(cudaStreamSynchronize(copy));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         if (d_rgb[i]) cudaFree(d_rgb[i]);
         if (d_depth[i]) cudaFree(d_depth[i]);
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
@@ -192,7 +192,7 @@ int FrameIO::ensure(int npix)
     }
     d_cfold = nullptr;
     cap_pix = 0;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         CUDA_TRY(cudaMalloc(&d_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMalloc(&d_depth[i], (size_t)npix * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
@@ -223,7 +223,7 @@ int FrameIO::ensure_tiles(int H, int W)
     p.ty[0] = (H + 7) / 8;
     off[0] = total;
     total += (size_t)p.tx[0] * p.ty[0] * sizeof(float);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         scratch_slot[i] = nullptr;
         CUDA_TRY(cudaMalloc(&scratch_slot[i], total));
@@ -253,21 +253,21 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     int rc = ensure(npix);
     if (rc) return rc;
     const int s = next;
-    next ^= 1;
+    next = (next + 1) % FRAME_SLOTS;
     const bool pinned = is_pinned_host(rgb) && is_pinned_host(depth);
     const uint8_t *src_rgb = rgb;
     const double *src_depth = depth;
     if (!pinned) {
-        // the staging slot was last read by the H2D copy issued two frames ago
+        // the staging slot was last read by the H2D copy issued FRAME_SLOTS frames ago
         CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
         memcpy(h_rgb[s], rgb, (size_t)npix * 3);
         memcpy(h_depth[s], depth, (size_t)npix * sizeof(double));
         src_rgb = h_rgb[s];
         src_depth = h_depth[s];
     }
-    // the device slot was last read by the kernels of the frame two calls ago
+    // the device slot was last read by the kernels of the frame FRAME_SLOTS calls ago
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
-    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
+    for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth[s], src_depth, (size_t)npix * sizeof(double), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -286,7 +286,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
     int rc = ensure(npix);
     if (rc) return rc;
     const int s = next;
-    next ^= 1;
+    next = (next + 1) % FRAME_SLOTS;
     const bool pinned = is_pinned_host(rgb) && is_pinned_host(depth_raw);
     const uint8_t *src_rgb = rgb;
     const uint16_t *src_depth = depth_raw;
@@ -298,7 +298,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
         src_depth = reinterpret_cast<const uint16_t *>(h_depth[s]);
     }
     CUDA_TRY(cudaStreamWaitEvent(copy, slot_free[s], 0));
-    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
+    for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(copy, side_slot_free[k][s], 0));
     CUDA_TRY(cudaMemcpyAsync(d_depth16[s], src_depth, (size_t)npix * sizeof(uint16_t), cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
@@ -314,13 +314,13 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
 
 int FrameIO::begin_kernels()
 {
-    slot ^= 1;
+    slot = (slot + 1) % FRAME_SLOTS;
     d_cfold = cfold_slot[slot];
     fs = reinterpret_cast<FrameScratch *>(scratch_slot[slot]);
     pyr = pyr_slot[slot];
-    // the integrate kernel of the frame two calls ago was the last reader of this slot
+    // the integrate kernels of the frame FRAME_SLOTS calls ago were the last readers of this slot
     CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
-    for (int k = 0; k < MAX_SIDE; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
+    for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
     CUDA_TRY(cudaEventRecord(k_begin, pre));
     CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
@@ -381,6 +381,7 @@ int FrameIO::end_kernels()
     CUDA_TRY(cudaEventRecord(k_end, compute));
     CUDA_TRY(cudaEventRecord(int_done[slot], compute));
     ended_side = n_side;
+    if (n_side > side_used) side_used = n_side;
     for (int k = 0; k < n_side; ++k) {
         CUDA_TRY(cudaEventRecord(side_end[k], side[k]));
         CUDA_TRY(cudaEventRecord(side_int_done[k][slot], side[k]));
@@ -416,7 +417,7 @@ void FrameIO::release()
     if (compute) cudaStreamSynchronize(compute);
     sync_side();
     if (copy) cudaStreamSynchronize(copy);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         for (int k = 0; k < MAX_SIDE; ++k) {
             if (side_int_done[k][i]) cudaEventDestroy(side_int_done[k][i]);
             if (side_slot_free[k][i]) cudaEventDestroy(side_slot_free[k][i]);
@@ -449,7 +450,7 @@ void FrameIO::release()
 int CounterStore::init(int n_warps)
 {
     n = n_warps;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         CUDA_TRY(cudaMalloc(&frame[i], (size_t)n * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(frame[i], 0, (size_t)n * sizeof(unsigned long long)));
     }
@@ -462,7 +463,7 @@ int CounterStore::init(int n_warps)
 
 void CounterStore::release()
 {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < FRAME_SLOTS; ++i)
         if (frame[i]) cudaFree(frame[i]);
     if (total) cudaFree(total);
     if (d_stats) cudaFree(d_stats);
@@ -509,7 +510,7 @@ struct tsdf_grid {
     int64_t n_x_local = 0;     // local voxel rows
     size_t nbricks = 0;
     float *bricks = nullptr;
-    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity: classes x [class_cap]
+    BrickRef *vis_list[FRAME_SLOTS] = {}; // one per frame slot: classes x [class_cap]
     int classes = 2;           // independent classes of bricks (1..DENSE_MAX_CLASSES), one integrate kernel each
     size_t class_cap = 0;      // capacity of one class's list inside vis_list[]
     Totals *tot = nullptr;
@@ -527,7 +528,7 @@ static int grid_free(tsdf_grid *g)
     g->io.release();
     g->geom.release();
     if (g->bricks) cudaFree(g->bricks);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < FRAME_SLOTS; ++i)
         if (g->vis_list[i]) cudaFree(g->vis_list[i]);
     if (g->tot) cudaFree(g->tot);
     g->counters.release();
@@ -571,11 +572,13 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
         tsdf_set_error("too many bricks per rank (%zu)", g->nbricks);
         return TSDF_ERR_BAD_ARG;
     }
+    static_assert(FRAME_SLOTS == 3, "vis_list allocation below assumes three frame slots");
     cudaError_t e;
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
     if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&g->vis_list[0], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&g->vis_list[1], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&g->vis_list[2], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
         cudaGetLastError();

@@ -11,7 +11,7 @@ struct tsdf_hash {
     FrameIO io;
     HashDev dev{};
     int64_t table_slots = 0, heap_blocks = 0;
-    BrickRef *vis_list[2] = {nullptr, nullptr}; // one per frame parity
+    BrickRef *vis_list[FRAME_SLOTS] = {}; // one per frame slot
     Totals *tot = nullptr;
     int *scratch_count = nullptr; // device int used by export / remove
     CounterStore counters;
@@ -36,7 +36,8 @@ static int hash_free(tsdf_hash *h)
     h->io.release();
     h->geom.release();
     void *ptrs[] = {h->dev.keys, h->dev.vals, h->dev.entries, h->dev.n_entries, h->dev.heap, h->dev.heap_top,
-                    h->dev.blocks, h->dev.known, h->vis_list[0], h->vis_list[1], h->tot, h->scratch_count, h->sb_flags};
+                    h->dev.blocks, h->dev.known, h->vis_list[0], h->vis_list[1], h->vis_list[2], h->tot, h->scratch_count,
+                    h->sb_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     h->counters.release();
@@ -85,6 +86,9 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
     d.nsx = (d.nbx + 3) / 4; d.nsy = (d.nby + 3) / 4; d.nsz = (d.nbz + 3) / 4;
     const size_t known_words = ((size_t)d.nbx * d.nby * d.nbz + 31) / 32;
     h->sb_words = ((size_t)d.nsx * d.nsy * d.nsz + 31) / 32;
+    // a key exists at most once per block of the bounded grid: that bounds the visible list too
+    const size_t list_cap = (size_t)std::min<int64_t>(S, (int64_t)d.nbx * d.nby * d.nbz);
+    static_assert(FRAME_SLOTS == 3, "vis_list allocation below assumes three frame slots");
     cudaError_t e;
     if ((e = cudaMalloc(&d.keys, S * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc(&d.vals, S * sizeof(uint32_t))) != cudaSuccess ||
@@ -95,8 +99,9 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&d.known, known_words * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&h->sb_flags, h->sb_words * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list[0], S * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list[1], S * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list[0], list_cap * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list[1], list_cap * sizeof(BrickRef))) != cudaSuccess ||
+        (e = cudaMalloc(&h->vis_list[2], list_cap * sizeof(BrickRef))) != cudaSuccess ||
         (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
         (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
         tsdf_set_error("device allocation failed (%lld slots, %lld blocks = %.2f GB): %s", (long long)S,

@@ -51,8 +51,9 @@ struct VolumeGeom {
 int tsdf_select_device(int device, int *sm_count);
 
 // Per-warp update counters owned by a handle (see UpdateCounters).
+#define FRAME_SLOTS 3 // frames in flight per handle: preparation of frame n+2 may start while frame n integrates
 struct CounterStore {
-    unsigned long long *frame[2] = {nullptr, nullptr}; // one per frame parity
+    unsigned long long *frame[FRAME_SLOTS] = {}; // one per frame slot
     unsigned long long *total = nullptr;
     int n = 0;
     int init(int n_warps);
@@ -75,8 +76,9 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
 //  * Per-frame preparation kernels (colour fold, tile pyramid, culling / ray walk, compaction) run
 //    on the `pre` stream, the integrate kernel on `compute` (the dense grid's second, independent
 //    classes of bricks on the `side` streams).  All per-frame scratch (folded colour,
-//    FrameScratch, tile pyramid, and the handles' visible lists) is double-buffered by frame
-//    parity, so the preparation of frame n+1 overlaps the integration of frame n.
+//    FrameScratch, tile pyramid, and the handles' visible lists) exists FRAME_SLOTS times, so
+//    the preparation of frames n+1 and n+2 overlaps the integration of frame n (the preparation
+//    chain is three dependent launches; with two slots it sat on the critical path of short frames).
 struct FrameIO {
     cudaStream_t compute = nullptr, copy = nullptr, pre = nullptr;
     // sibling integrate streams of the dense grid (independent classes of bricks, see k_cull_bricks);
@@ -84,29 +86,30 @@ struct FrameIO {
     static const int MAX_SIDE = DENSE_MAX_CLASSES - 1;
     cudaStream_t side[MAX_SIDE] = {};
     int n_side = 0;
-    cudaEvent_t side_int_done[MAX_SIDE][2] = {}, side_slot_free[MAX_SIDE][2] = {}, side_end[MAX_SIDE] = {};
+    cudaEvent_t side_int_done[MAX_SIDE][FRAME_SLOTS] = {}, side_slot_free[MAX_SIDE][FRAME_SLOTS] = {}, side_end[MAX_SIDE] = {};
     bool side_pending[MAX_SIDE] = {}; // work issued on side[k] that `compute` has not been made to wait for
     int ended_side = 0;               // side streams used by the last frame issued (for last_ms)
+    int side_used = 0;                // side streams ever used: their events are the only ones worth waiting on
     int cap_pix = 0;
-    uint8_t *d_rgb[2] = {nullptr, nullptr};
-    double *d_depth[2] = {nullptr, nullptr};
-    uint8_t *h_rgb[2] = {nullptr, nullptr};
-    double *h_depth[2] = {nullptr, nullptr};
-    uint16_t *d_depth16[2] = {nullptr, nullptr}; // raw sensor depth (frame ingest path)
-    // per-frame scratch, one set per frame parity: [FrameScratch | tile pyramid levels 1..3]
+    uint8_t *d_rgb[FRAME_SLOTS] = {};
+    double *d_depth[FRAME_SLOTS] = {};
+    uint8_t *h_rgb[FRAME_SLOTS] = {};
+    double *h_depth[FRAME_SLOTS] = {};
+    uint16_t *d_depth16[FRAME_SLOTS] = {}; // raw sensor depth (frame ingest path)
+    // per-frame scratch, one set per frame slot: [FrameScratch | tile pyramid levels 1..3]
     // (cleared every frame), then pyramid level 0
-    uint32_t *cfold_slot[2] = {nullptr, nullptr};
-    uint8_t *scratch_slot[2] = {nullptr, nullptr};
-    TilePyramid pyr_slot[2] = {};
+    uint32_t *cfold_slot[FRAME_SLOTS] = {};
+    uint8_t *scratch_slot[FRAME_SLOTS] = {};
+    TilePyramid pyr_slot[FRAME_SLOTS] = {};
     size_t clear_bytes = 0;
-    int slot = 1; // parity of the frame being issued (toggled by begin_kernels)
+    int slot = FRAME_SLOTS - 1; // scratch slot of the frame being issued (advanced by begin_kernels)
     // views of the current slot (after a frame: of the last frame issued)
     uint32_t *d_cfold = nullptr;
     FrameScratch *fs = nullptr;
     TilePyramid pyr{};
     int tiles_H = 0, tiles_W = 0;
-    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
-    cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done[FRAME_SLOTS] = {}, slot_free[FRAME_SLOTS] = {};
+    cudaEvent_t pre_done[FRAME_SLOTS] = {}, int_done[FRAME_SLOTS] = {};
     cudaEvent_t k_begin = nullptr, k_end = nullptr;
     cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
     int n_marks = 0;
@@ -124,7 +127,7 @@ struct FrameIO {
                    const uint8_t **d_rgb_out, const double **d_depth_out);
     int ensure_cfold(int npix);
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
-    // picks the frame's scratch slot, waits (on `pre`) until the frame two calls ago has left it,
+    // picks the frame's scratch slot, waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it,
     // clears FrameScratch + pyramid levels 1..3
     int begin_kernels();
     int prepared();    // preparation kernels issued: `compute` waits for them
