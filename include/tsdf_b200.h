@@ -89,13 +89,14 @@ int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs);
  * [2] bricks visited by the last frame, [3] frames integrated. */
 int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4]);
 int tsdf_grid_sync(tsdf_grid *g);
-/* Milliseconds the device spent on the last integrate call's kernels (CUDA events on the
- * handle's stream; waits for them). */
-int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms);
-/* Measurement aids.  set_profiling(1) records an extra event between the frame-preparation
- * kernels (colour fold, brick culling) and the integrate kernel; last_stage_ms then returns
- * n = 2 durations {prepare+cull, integrate} of the last frame (n = 1: the whole frame).
+/* Measurement aids.  Timing events are recorded only while profiling is on:
+ *   set_profiling(2): frame timing -- last_kernel_ms() = device milliseconds from the first
+ *     preparation kernel to the end of the last integrate kernel of the last frame (waits for it);
+ *   set_profiling(1): stage timing -- additionally the frame's integrate kernels run on one stream
+ *     behind an extra event, and last_stage_ms() returns n = 2 durations {prepare+cull, integrate};
+ *   set_profiling(0) (default): no timing events (three API calls less per frame).
  * stream() exposes the handle's cudaStream_t so callers can record their own events on it. */
+int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms);
 int tsdf_grid_set_profiling(tsdf_grid *g, int on);
 int tsdf_grid_last_stage_ms(tsdf_grid *g, float ms[4], int *n);
 int tsdf_grid_stream(tsdf_grid *g, void **stream);

@@ -11,6 +11,7 @@ frames, K = synth.room_stream(nfr, room, seed=0)
 vol = grid_fusion.TSDFVolume(room.copy(), vs)
 dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), np.linalg.inv(p)) for c, d, p in frames]
 torch.cuda.synchronize()
+vol.set_profiling(True, frame_only=True)
 H, W = frames[0][1].shape
 REPS = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 for rep in range(REPS):

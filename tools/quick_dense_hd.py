@@ -9,6 +9,7 @@ frames, K = synth.room_stream(4, room, width=W, height=H, seed=1)
 vol = grid_fusion.TSDFVolume(room.copy(), 0.02)
 dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(d).cuda(), np.linalg.inv(p)) for c, d, p in frames]
 torch.cuda.synchronize()
+vol.set_profiling(True, frame_only=True)
 REPS = 30
 for rep in range(REPS):
     for dc, dd, ti in dev:

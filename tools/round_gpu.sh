@@ -17,4 +17,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 24 --warmup 3 --no-cpu > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate_dense -s 80 -c 2 -f -o $O/${TAG}_dense_full \
     python tools/quick_dense.py 0.01 16 3 > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 300 python tools/quick_classes.py 8 1 2>&1 | grep world > $O/${TAG}_classes.log; cat $O/${TAG}_classes.log
 ls -la $O | tail -n 12

@@ -321,7 +321,7 @@ int FrameIO::begin_kernels()
     // the integrate kernels of the frame FRAME_SLOTS calls ago were the last readers of this slot
     CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
     for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
-    CUDA_TRY(cudaEventRecord(k_begin, pre));
+    if (timing) CUDA_TRY(cudaEventRecord(k_begin, pre));
     CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
     return TSDF_OK;
@@ -339,8 +339,8 @@ int FrameIO::join()
 {
     for (int k = 0; k < MAX_SIDE; ++k) {
         if (!side_pending[k]) continue;
-        // side_end[k] is the last event recorded on side[k]
-        CUDA_TRY(cudaStreamWaitEvent(compute, side_end[k], 0));
+        // the last event recorded on side[k]
+        CUDA_TRY(cudaStreamWaitEvent(compute, side_int_done[k][side_slot_last], 0));
         side_pending[k] = false;
     }
     return TSDF_OK;
@@ -364,7 +364,7 @@ int FrameIO::mark()
 int FrameIO::last_stage_ms(float ms[4], int *n)
 {
     BAD_ARG(!ms || !n, "NULL argument");
-    BAD_ARG(!timed, "no frame integrated yet");
+    BAD_ARG(!timed, "no frame has been timed (switch profiling on before the frame)");
     CUDA_TRY(cudaEventSynchronize(k_end));
     cudaEvent_t ev[5];
     int k = 0;
@@ -378,16 +378,17 @@ int FrameIO::last_stage_ms(float ms[4], int *n)
 
 int FrameIO::end_kernels()
 {
-    CUDA_TRY(cudaEventRecord(k_end, compute));
+    if (timing) CUDA_TRY(cudaEventRecord(k_end, compute));
     CUDA_TRY(cudaEventRecord(int_done[slot], compute));
     ended_side = n_side;
     if (n_side > side_used) side_used = n_side;
+    if (n_side) side_slot_last = slot;
     for (int k = 0; k < n_side; ++k) {
-        CUDA_TRY(cudaEventRecord(side_end[k], side[k]));
+        if (timing) CUDA_TRY(cudaEventRecord(side_end[k], side[k]));
         CUDA_TRY(cudaEventRecord(side_int_done[k][slot], side[k]));
         side_pending[k] = true;
     }
-    timed = true;
+    timed = timing;
     if (cur >= 0) {
         CUDA_TRY(cudaEventRecord(slot_free[cur], compute));
         for (int k = 0; k < n_side; ++k) CUDA_TRY(cudaEventRecord(side_slot_free[k][cur], side[k]));
@@ -399,7 +400,7 @@ int FrameIO::end_kernels()
 int FrameIO::last_ms(float *ms)
 {
     BAD_ARG(!ms, "ms is NULL");
-    BAD_ARG(!timed, "no frame integrated yet");
+    BAD_ARG(!timed, "no frame has been timed (switch profiling on before the frame)");
     CUDA_TRY(cudaEventSynchronize(k_end));
     CUDA_TRY(cudaEventElapsedTime(ms, k_begin, k_end));
     for (int k = 0; k < ended_side; ++k) { // sibling integrate kernels of the frame: whichever ended last
@@ -566,6 +567,7 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     // measurement knobs (profiles/r1_dense_classes.md); the defaults are the measured best
     if (const char *e = getenv("TSDF_DENSE_CLASSES")) g->classes = std::min(DENSE_MAX_CLASSES, std::max(1, atoi(e)));
     // (lbx + by + bz) % classes: every z-column holds at most ceil(nbz / classes) bricks of a class
+    g->io.timing = false; // see tsdf_grid_set_profiling
     g->class_cap = (size_t)g->nlbx * g->geom.nb[1] * ((g->geom.nb[2] + g->classes - 1) / g->classes);
     if (g->nbricks >= (size_t)1 << 31) {
         grid_free(g);
@@ -788,11 +790,15 @@ extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)
 extern "C" int tsdf_grid_set_profiling(tsdf_grid *g, int on)
 {
     BAD_ARG(!g, "NULL handle");
-    if (g->profile_stages != (on != 0)) { // the integrate kernels change streams: drain both first
+    BAD_ARG(on < 0 || on > 2, "profiling mode %d (0 off, 1 stages, 2 frame time only)", on);
+    const bool stages = on == 1;
+    if (g->profile_stages != stages) { // the integrate kernels change streams: drain all of them first
         int rc = tsdf_grid_sync(g);
         if (rc) return rc;
     }
-    g->profile_stages = on != 0;
+    g->profile_stages = stages;
+    g->io.timing = on != 0;
+    g->io.timed = false;
     return TSDF_OK;
 }
 

@@ -89,6 +89,7 @@ struct FrameIO {
     cudaEvent_t side_int_done[MAX_SIDE][FRAME_SLOTS] = {}, side_slot_free[MAX_SIDE][FRAME_SLOTS] = {}, side_end[MAX_SIDE] = {};
     bool side_pending[MAX_SIDE] = {}; // work issued on side[k] that `compute` has not been made to wait for
     int ended_side = 0;               // side streams used by the last frame issued (for last_ms)
+    int side_slot_last = 0;           // frame slot whose side_int_done events were recorded last
     int side_used = 0;                // side streams ever used: their events are the only ones worth waiting on
     int cap_pix = 0;
     uint8_t *d_rgb[FRAME_SLOTS] = {};
@@ -115,6 +116,9 @@ struct FrameIO {
     int n_marks = 0;
     int next = 0, cur = -1;
     bool timed = false;
+    // Frame timing events (k_begin / k_end / side_end) cost three API calls per frame; the dense
+    // handle records them only while timing or stage profiling is switched on.
+    bool timing = true;
 
     int init();
     int ensure(int npix);

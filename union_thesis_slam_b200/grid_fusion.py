@@ -173,8 +173,12 @@ class TSDFVolume:
         _capi.check(self._lib.tsdf_grid_last_kernel_ms(self._handle, C.byref(ms)))
         return ms.value
 
-    def set_profiling(self, on=True):
-        _capi.check(self._lib.tsdf_grid_set_profiling(self._handle, int(bool(on))))
+    def set_profiling(self, on=True, frame_only=False):
+        """Timing events are off by default (they cost API calls per frame).  ``on``: stage
+        timing for last_stage_ms() (the frame's integrate kernels then share one stream);
+        ``frame_only``: just the whole-frame time for last_kernel_ms(), streams as in production."""
+        mode = 0 if not on else (2 if frame_only else 1)
+        _capi.check(self._lib.tsdf_grid_set_profiling(self._handle, mode))
 
     def last_stage_ms(self):
         """Device milliseconds of the last frame's stages: [prepare+cull, integrate] with
