@@ -206,6 +206,18 @@ int vbt_double_table_size(tsdf_buckets *h);
 /* stats[0] buckets (table size), [1] non-empty buckets, [2] entries stored, [3] buckets holding
  * more than one entry (get_num_collisions), [4] resizes so far, [5] bucket size. */
 int vbt_stats(tsdf_buckets *h, int64_t stats[6]);
+/* The reference's HashTable.integrate as a whole (hash_fusion.py:103-145) on the per-voxel container:
+ * every voxel of the bounded volume is projected in vox_coords order with the reference's own
+ * arithmetic, the voxels it would update are streamed in that order through the per-voxel loop
+ * (look-up, insert on a miss, float64 running mean).  obs_weight does not exist here: the reference
+ * never passes it on (:141, :145).  Frame arguments as tsdf_grid_integrate (host pointers).
+ * *n_valid (may be NULL): voxels updated by the frame. */
+int vbt_integrate_frame(tsdf_buckets *h, const int64_t dim[3], const float origin[3], double voxel_size, double trunc,
+                        const uint8_t *rgb, const double *depth, int H, int W, const double K[9], const double Tinv[16],
+                        int64_t *n_valid);
+/* get_volume of the reference hash map (hash_fusion.py:442-463): [X][Y][Z] float32 planes, tsdf 1 /
+ * colour 0 where no entry is stored, else float32(sdf) / float32(colour) of the entry's voxel. */
+int vbt_to_dense(tsdf_buckets *h, const int64_t dim[3], float *tsdf, float *color);
 /* Slot layout in (bucket, slot) order.  rows == NULL: only *count.  rows[count][7] =
  * {bucket, slot, x, y, z, offset bucket, offset slot} (-1, -1 = empty offset); voxels (may be
  * NULL) [count][3] = (sdf, colour, weight), NaN sdf for an entry stored without a voxel. */

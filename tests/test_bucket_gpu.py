@@ -214,3 +214,79 @@ def test_bad_arguments_raise():
         vt.apply([bo.OP_ADD], [[1 << 40, 0, 0]])
     assert vt.get_hash_entry([1, 2, 3]) is None and vt.remove_hash_entry(bucket_table.HashEntry([1, 2, 3], None, None)) == 0
     vt.close()
+
+
+# ---- HashTable(per_voxel=True): the reference's whole integrate path on its own data structure ----
+def _feed_layout_oracle(orc_table, hashvox, before_weight):
+    """Replays one frame's insertions into the container oracle: the voxels the frame updated, in
+    vox_coords order (C order of the volume), looked up and inserted on a miss (hash_fusion.py:135-145)."""
+    for v in np.argwhere(hashvox.weight != before_weight):
+        if orc_table.find(v)[0] < 0:
+            orc_table.add(v)
+
+
+def test_per_voxel_mode_reproduces_reference_hash_table_config1():
+    """Bundled frames 0..2 at config 1 (405 x 264 x 289 @ 2 cm, 1 000 000 buckets): entry count,
+    non-empty buckets, collisions and the sha256 of both get_volume() planes are the numbers the
+    UNMODIFIED reference HashTable produced (tests/golden/golden.json, made by make_golden.py)."""
+    import frames
+    import scenes
+    from union_thesis_slam_b200 import hash_fusion
+    gold = frames.golden()["hash"]
+    K = frames.intrinsics()
+    ht = hash_fusion.HashTable(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL, map_size=1000000, per_voxel=True)
+    for n in range(3):
+        c, d, p = frames.load_frame(n)
+        ht.integrate(c, d, K, p)
+        g = gold[str(n + 1)]
+        assert ht.count_num_hash_entries() == g["entries"]
+        assert ht.get_num_non_empty_bucket() == g["non_empty_buckets"]
+        assert ht.get_num_collisions() == g["collisions"]
+        assert ht.voxel_table.stats()["table_size"] == g["table_size"]
+        t, col = ht.get_volume()
+        assert frames.sha(t) == g["tsdf"] and frames.sha(col) == g["color"], "frame %d" % n
+    ht.close()
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_per_voxel_mode_small_reference_fixtures(seed):
+    """Full outputs of the reference HashTable on small cases (map_size 20 000, so the table resizes)."""
+    from union_thesis_slam_b200 import hash_fusion
+    z = np.load(os.path.join(HERE, "golden", "small_hash_%d.npz" % seed))
+    ht = hash_fusion.HashTable(z["vol_bnds"].copy(), float(z["voxel_size"]), map_size=20000, per_voxel=True)
+    for c, d, p, obs in zip(z["color"], z["depth"], z["pose"], z["obs"]):
+        ht.integrate(c, d, z["K"], p, obs_weight=float(obs))
+    t, col = ht.get_volume()
+    assert np.array_equal(t, z["tsdf"]) and np.array_equal(col, z["color_vol"])
+    rows = ht.voxel_table.layout()
+    assert np.array_equal(np.array(sorted(rows[:, 2:5].tolist()), np.int64), z["entries"])
+    st = ht.voxel_table.stats()
+    assert st["table_size"] == int(z["table_size"]) and st["non_empty_buckets"] == int(z["non_empty"])
+    ht.close()
+
+
+def test_per_voxel_mode_matches_oracles_on_random_case():
+    """Slot layout against the container oracle, float64 state against the per-voxel hash oracle."""
+    import scenes
+    from oracle import oracle
+    from union_thesis_slam_b200 import hash_fusion
+    case = scenes.small_case(seed=91, dims=(33, 41, 27), voxel_size=0.02, hw=(60, 80), nframes=4)
+    ht = hash_fusion.HashTable(case["vol_bnds"].copy(), case["voxel_size"], map_size=3000, per_voxel=True)
+    oh = oracle.OracleHashVox(case["vol_bnds"].copy(), case["voxel_size"])
+    ot = bo.OracleBucketTable(3000)
+    for c, d, p, obs in case["frames"]:
+        before = oh.weight.copy()
+        n = oh.integrate(c, d, case["K"], p, obs_weight=obs)
+        _feed_layout_oracle(ot, oh, before)
+        got = ht.voxel_table.integrate_frame(ht._vol_dim, ht._vol_origin, ht._voxel_size, ht._trunc_margin, c, d, case["K"], p)
+        assert got == n
+    t, col = ht.get_volume()
+    et, ec = oh.get_volume()
+    assert np.array_equal(t, et) and np.array_equal(col, ec)
+    rows, vox = ht.voxel_table.layout(with_voxels=True)
+    assert rows.tolist() == [list(r) for r in ot.layout()]
+    idx = tuple(rows[:, 2:5].T)
+    assert np.array_equal(vox[:, 0], oh.sdf[idx]) and np.array_equal(vox[:, 2], oh.weight[idx])
+    assert np.array_equal(vox[:, 1], oh.color[idx])
+    assert ht.voxel_table.stats()["resizes"] == ot.resizes >= 1
+    ht.close()

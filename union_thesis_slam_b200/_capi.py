@@ -58,6 +58,8 @@ SYMBOLS = [
     ("vbt_double_table_size", _i, [_p]),
     ("vbt_stats", _i, [_p, _p]),
     ("vbt_dump", _i, [_p, _i64, _p, _p, _p]),
+    ("vbt_integrate_frame", _i, [_p, _p, _p, _d, _d, _p, _p, _i, _i, _p, _p, _p]),
+    ("vbt_to_dense", _i, [_p, _p, _p, _p]),
     ("tsdf_mesh_extract", _i, [_p, _p, _p, _d, _p, _i, _pp, _p, _p]),
     ("tsdf_mesh_download", _i, [_p, _p, _p, _p, _p]),
     ("tsdf_mesh_destroy", _i, [_p]),

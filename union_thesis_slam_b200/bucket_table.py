@@ -125,6 +125,31 @@ class VoxelBucketTable:
         args[:, 1] = colors
         return self.apply(np.full(len(pos), OP_INTEGRATE, np.int32), pos, args)
 
+    def integrate_frame(self, vol_dim, vol_origin, voxel_size, trunc_margin, color_im, depth_im, cam_intr, cam_pose):
+        """The reference's ``HashTable.integrate`` as a whole (hash_fusion.py:103-145): the voxels the
+        frame updates, in ``vox_coords`` order, through the per-voxel loop.  Returns their number."""
+        im_h, im_w = depth_im.shape
+        dim = np.ascontiguousarray(vol_dim, dtype=np.int64)
+        origin = np.ascontiguousarray(vol_origin, dtype=np.float32)
+        rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth_im, dtype=np.float64)
+        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
+        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))  # hash_fusion.py:112
+        n = C.c_int64()
+        _capi.check(self._lib.vbt_integrate_frame(
+            self._handle, _capi.ptr(dim), _capi.ptr(origin), float(voxel_size), float(trunc_margin), _capi.ptr(rgb),
+            _capi.ptr(depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv), C.byref(n)))
+        return n.value
+
+    def to_dense(self, vol_dim):
+        """(tsdf, colour) float32 [X,Y,Z] volumes of the stored voxels (hash_fusion.py:442-463)."""
+        dim = np.ascontiguousarray(vol_dim, dtype=np.int64)
+        shape = tuple(int(d) for d in dim)
+        t = np.empty(shape, np.float32)
+        c = np.empty(shape, np.float32)
+        _capi.check(self._lib.vbt_to_dense(self._handle, _capi.ptr(dim), _capi.ptr(t), _capi.ptr(c)))
+        return t, c
+
     # -- reference container methods ---------------------------------------------------------------
     def hash_function(self, world_coord):
         """H(x,y,z) = (x*p1 xor y*p2 xor z*p3) mod n (hash_fusion.py:182-190)."""

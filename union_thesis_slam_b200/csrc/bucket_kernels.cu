@@ -273,13 +273,14 @@ __device__ void vbt_voxel_integrate(double &sdf, double &col, double &wgt, doubl
 // that op with skip_check = 1 (the reference does not re-check after resizing).
 //   pos[i][3] int32; args[i][5] = {dist, colour, sdf, col, wgt} (INTEGRATE uses 0..1, ADD uses 2..4)
 //   out[i][2]: ADD/GET/INTEGRATE -> (bucket, slot) or (-1, -1); REMOVE -> (1 / 0, -1)
+//   ops == nullptr: every op is INTEGRATE (the per-frame voxel stream); out == nullptr: no results wanted
 __global__ void k_vbt_apply(BucketDev t, double load_factor, const int32_t *__restrict__ ops,
                             const int32_t *__restrict__ pos, const double *__restrict__ args, long long begin,
                             long long n, int skip_check, long long *__restrict__ out, VbtStatus *st)
 {
     if (blockIdx.x || threadIdx.x) return;
     for (long long i = begin; i < n; ++i) {
-        const int op = ops[i];
+        const int op = ops ? ops[i] : VBT_INTEGRATE;
         const int x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
         long long rb = -1;
         int re = -1;
@@ -319,7 +320,7 @@ __global__ void k_vbt_apply(BucketDev t, double load_factor, const int32_t *__re
             st->next = i; st->code = VBT_DANGLING;
             return;
         }
-        out[2 * i] = rb; out[2 * i + 1] = re;
+        if (out) { out[2 * i] = rb; out[2 * i + 1] = re; }
     }
     st->next = n; st->code = VBT_DONE;
 }
@@ -394,6 +395,118 @@ __global__ void k_vbt_init(BucketDev t)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The pre-pass of the reference's HashTable.integrate (hash_fusion.py:108-132) as an ORDERED voxel
+// stream: every voxel of the bounded volume in vox_coords order (x slowest, z fastest,
+// hash_fusion.py:58-69) is projected with the reference's own chain (exact_pixel: dgemm-ordered
+// transform, IEEE division, rint), and the voxels with valid_pts set are emitted in that order with
+// their dist = min(1, depth_diff / trunc) (float64) and the folded colour of their pixel.  Order
+// matters: it is the insertion order of the container, hence its slot layout.
+// Two passes over the same test (count per 256-voxel chunk, exclusive scan, ordered emit).
+#define VS_CHUNK 256
+__device__ __forceinline__ bool voxel_valid(const FrameParams &f, const VolumeParams &v, long long i, int &x, int &y, int &z,
+                                            int &pix, double &dist)
+{
+    z = (int)(i % v.dim_z);
+    y = (int)((i / v.dim_z) % v.dim_y);
+    x = (int)(i / ((long long)v.dim_z * v.dim_y));
+    const double wx = v.lat_x[x], wy = v.lat_y[y], wz = v.lat_z[z];
+    const double Z = __dadd_rn(__fma_rn(f.T[10], wz, __fma_rn(f.T[9], wy, __dmul_rn(f.T[8], wx))), f.T[11]);
+    if (!(Z > 0.0)) return false; // hash_fusion.py:119
+    pix = exact_pixel(f.T[0], f.T[1], f.T[2], f.T[3], f.T[4], f.T[5], f.T[6], f.T[7], wx, wy, wz, Z, f.fx, f.fy, f.cx, f.cy,
+                      f.W, f.H);
+    if (pix < 0) return false;
+    const double d = f.depth[pix];
+    const double diff = __dadd_rn(d, -Z);
+    if (!(d > 0.0 && diff >= f.neg_trunc)) return false; // hash_fusion.py:124
+    dist = fmin(1.0, __ddiv_rn(diff, f.trunc));           // hash_fusion.py:125
+    return true;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(VS_CHUNK)
+k_voxel_stream(FrameParams f, VolumeParams v, const uint8_t *__restrict__ rgb, long long n_vox, unsigned *__restrict__ counts,
+               const unsigned long long *__restrict__ offsets, int32_t *__restrict__ pos_out, double *__restrict__ args_out)
+{
+    __shared__ unsigned s_warp[VS_CHUNK / 32];
+    const long long i = (long long)blockIdx.x * VS_CHUNK + threadIdx.x;
+    int x = 0, y = 0, z = 0, pix = 0;
+    double dist = 0.0;
+    const bool valid = i < n_vox && voxel_valid(f, v, i, x, y, z, pix, dist);
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (!EMIT) {
+        if (threadIdx.x == 0) {
+            unsigned c = 0;
+            for (int w = 0; w < VS_CHUNK / 32; ++w) c += s_warp[w];
+            counts[blockIdx.x] = c;
+        }
+        return;
+    }
+    if (!valid) return;
+    unsigned before = __popc(ballot & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const unsigned long long k = offsets[blockIdx.x] + before;
+    pos_out[3 * k] = x; pos_out[3 * k + 1] = y; pos_out[3 * k + 2] = z;
+    // hash_fusion.py:109-110: floor(B * 65536 + G * 256 + R) of the float32 image, an exact integer
+    const unsigned r = rgb[3 * pix], g = rgb[3 * pix + 1], b = rgb[3 * pix + 2];
+    args_out[5 * k] = dist;
+    args_out[5 * k + 1] = (double)((b << 16) | (g << 8) | r);
+    args_out[5 * k + 2] = 0.0; args_out[5 * k + 3] = 0.0; args_out[5 * k + 4] = 0.0;
+}
+
+// Exclusive scan of the chunk counts by one block (tiles of 1024, running carry).
+__global__ void k_scan_counts(const unsigned *__restrict__ counts, unsigned long long *__restrict__ offsets, long long n,
+                              unsigned long long *total)
+{
+    __shared__ unsigned long long s[1024];
+    __shared__ unsigned long long carry;
+    const int t = threadIdx.x;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < n; base += 1024) {
+        const long long idx = base + t;
+        const unsigned long long val = idx < n ? counts[idx] : 0ull;
+        s[t] = val;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long add = t >= o ? s[t - o] : 0ull;
+            __syncthreads();
+            s[t] += add;
+            __syncthreads();
+        }
+        if (idx < n) offsets[idx] = carry + s[t] - val;
+        __syncthreads();
+        if (t == 1023) carry += s[1023];
+        __syncthreads();
+    }
+    if (t == 0) *total = carry;
+}
+
+// get_volume of the reference hash map (hash_fusion.py:442-463): tsdf = 1 / colour = 0 everywhere,
+// then every entry that carries a voxel writes float32(sdf), float32(colour) at its position.
+__global__ void k_vbt_fill_dense(float *tsdf, float *color, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        tsdf[i] = 1.0f;
+        color[i] = 0.0f;
+    }
+}
+__global__ void k_vbt_scatter_dense(BucketDev t, int dx, int dy, int dz, float *tsdf, float *color)
+{
+    const long long n = t.S * t.B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (!t.occ[i] || t.vox[3 * i] != t.vox[3 * i]) continue; // empty slot, or an entry without a voxel (NaN)
+        const int x = t.pos[3 * i], y = t.pos[3 * i + 1], z = t.pos[3 * i + 2];
+        if (x < 0 || y < 0 || z < 0 || x >= dx || y >= dy || z >= dz) continue;
+        const long long o = ((long long)x * dy + y) * dz + z;
+        tsdf[o] = (float)t.vox[3 * i];
+        color[o] = (float)t.vox[3 * i + 1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct tsdf_buckets {
     int device = 0;
     double load_factor = 0.75;
@@ -402,6 +515,18 @@ struct tsdf_buckets {
     VbtStatus *d_status = nullptr, *h_status = nullptr;
     unsigned long long *d_counts = nullptr;
     long long resizes = 0;
+    // per-frame voxel stream (vbt_integrate_frame): cached lattice tables and growable device buffers
+    VolumeGeom geom{};
+    bool geom_valid = false;
+    uint8_t *d_rgb = nullptr;
+    double *d_depth = nullptr;
+    size_t cap_pix = 0;
+    unsigned *d_chunk_counts = nullptr;
+    unsigned long long *d_chunk_offsets = nullptr, *d_total = nullptr;
+    size_t cap_chunks = 0;
+    int32_t *d_pos = nullptr;
+    double *d_args = nullptr;
+    size_t cap_stream = 0;
 };
 
 static void table_free(BucketDev &t)
@@ -480,6 +605,28 @@ static int do_resize(tsdf_buckets *h, int depth)
     return rc;
 }
 
+// Runs ops[0..n) (device arrays) in order, doubling the table whenever an insert finds it at its
+// load factor (the kernel stops there; the reference does not re-check after resizing).
+static int apply_device(tsdf_buckets *h, const int32_t *d_ops, const int32_t *d_pos, const double *d_args, long long n,
+                        long long *d_out)
+{
+    long long begin = 0;
+    int skip = 0;
+    while (true) {
+        k_vbt_apply<<<1, 32, 0, h->stream>>>(h->t, h->load_factor, d_ops, d_pos, d_args, begin, n, skip, d_out, h->d_status);
+        if (cudaGetLastError() != cudaSuccess) {
+            tsdf_set_error("bucket table: kernel launch failed");
+            return TSDF_ERR_CUDA;
+        }
+        VbtStatus st;
+        int rc = read_status(h, &st);
+        if (rc || st.code == VBT_DONE) return rc;
+        begin = st.next;
+        skip = 1;
+        if ((rc = do_resize(h, 0))) return rc;
+    }
+}
+
 extern "C" int vbt_create(int64_t n_buckets, int bucket_size, double load_factor, int device, tsdf_buckets **out)
 {
     BAD_ARG(!out, "out is NULL");
@@ -525,6 +672,10 @@ extern "C" int vbt_destroy(tsdf_buckets *h)
     if (h->d_status) cudaFree(h->d_status);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->d_counts) cudaFree(h->d_counts);
+    if (h->geom_valid) h->geom.release();
+    void *bufs[] = {h->d_rgb, h->d_depth, h->d_chunk_counts, h->d_chunk_offsets, h->d_total, h->d_pos, h->d_args};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TSDF_OK;
@@ -567,21 +718,7 @@ extern "C" int vbt_apply(tsdf_buckets *h, const int32_t *ops, const int64_t *pos
         cudaMemcpyAsync(d_pos, p32.data(), n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyAsync(d_args, a.data(), n * 5 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
         cudaMemsetAsync(d_out, 0xFF, n * 2 * sizeof(long long), h->stream);
-        long long begin = 0;
-        int skip = 0;
-        while (!rc) {
-            k_vbt_apply<<<1, 32, 0, h->stream>>>(h->t, h->load_factor, d_ops, d_pos, d_args, begin, n, skip, d_out, h->d_status);
-            VbtStatus st;
-            if (cudaGetLastError() != cudaSuccess) {
-                tsdf_set_error("bucket table: kernel launch failed");
-                rc = TSDF_ERR_CUDA;
-                break;
-            }
-            if ((rc = read_status(h, &st)) || st.code == VBT_DONE) break;
-            begin = st.next; // the insert at `begin` found the table at its load factor
-            skip = 1;
-            rc = do_resize(h, 0);
-        }
+        rc = apply_device(h, d_ops, d_pos, d_args, n, d_out);
     }
     if (!rc) {
         e = cudaMemcpyAsync(out, d_out, n * 2 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
@@ -696,6 +833,120 @@ extern "C" int vbt_dump(tsdf_buckets *h, int64_t capacity, int64_t *count, int64
         if (voxels)
             for (int c = 0; c < 3; ++c) voxels[3 * k + c] = vox[3 * i + c];
         ++k;
+    }
+    return TSDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's HashTable.integrate, whole (hash_fusion.py:103-145): ordered voxel stream of the
+// frame, then the per-voxel loop over it.  obs_weight does not exist here: the reference accepts it
+// and never passes it on (:141, :145).
+template <typename T>
+static int grow(T **buf, size_t *cap, size_t want, const char *what)
+{
+    if (want <= *cap && *buf) return TSDF_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    const size_t n = want + want / 4 + 64;
+    if (cudaMalloc(buf, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        tsdf_set_error("bucket table: device allocation of %s (%zu elements) failed", what, n);
+        return TSDF_ERR_OOM;
+    }
+    *cap = n;
+    return TSDF_OK;
+}
+
+extern "C" int vbt_integrate_frame(tsdf_buckets *h, const int64_t dim[3], const float origin[3], double voxel_size,
+                                   double trunc, const uint8_t *rgb, const double *depth, int H, int W, const double K[9],
+                                   const double Tinv[16], int64_t *n_valid)
+{
+    BAD_ARG(!h || !dim || !origin || !rgb || !depth, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if (!h->geom_valid || h->geom.dim[0] != dim[0] || h->geom.dim[1] != dim[1] || h->geom.dim[2] != dim[2] ||
+        h->geom.origin[0] != origin[0] || h->geom.origin[1] != origin[1] || h->geom.origin[2] != origin[2] ||
+        h->geom.vs != voxel_size || h->geom.trunc != trunc) {
+        if (h->geom_valid) h->geom.release();
+        h->geom_valid = false;
+        if ((rc = h->geom.init(dim, origin, voxel_size, trunc))) return rc;
+        h->geom_valid = true;
+    }
+    FrameParams f;
+    CullParams c;
+    if ((rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, 1.0))) return rc;
+    const size_t npix = (size_t)H * W;
+    {   // frame buffers share one capacity
+        size_t cap_a = h->cap_pix * 3, cap_b = h->cap_pix;
+        if ((rc = grow(&h->d_rgb, &cap_a, npix * 3, "colour image")) || (rc = grow(&h->d_depth, &cap_b, npix, "depth image")))
+            return rc;
+        h->cap_pix = std::min(cap_a / 3, cap_b);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_rgb, rgb, npix * 3, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_depth, depth, npix * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    f.depth = h->d_depth;
+    const VolumeParams v = h->geom.params();
+    const long long n_vox = (long long)dim[0] * dim[1] * dim[2];
+    const long long n_chunks = (n_vox + VS_CHUNK - 1) / VS_CHUNK;
+    BAD_ARG(n_chunks >= (1LL << 31), "volume too large for the per-voxel stream (%lld voxels)", n_vox);
+    {
+        size_t cap_a = h->cap_chunks, cap_b = h->cap_chunks, one = h->d_total ? 1 : 0;
+        if ((rc = grow(&h->d_chunk_counts, &cap_a, (size_t)n_chunks, "chunk counts")) ||
+            (rc = grow(&h->d_chunk_offsets, &cap_b, (size_t)n_chunks, "chunk offsets")) ||
+            (rc = grow(&h->d_total, &one, 1, "stream length")))
+            return rc;
+        h->cap_chunks = std::min(cap_a, cap_b);
+    }
+    k_voxel_stream<false><<<(unsigned)n_chunks, VS_CHUNK, 0, h->stream>>>(f, v, h->d_rgb, n_vox, h->d_chunk_counts, nullptr,
+                                                                          nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    k_scan_counts<<<1, 1024, 0, h->stream>>>(h->d_chunk_counts, h->d_chunk_offsets, n_chunks, h->d_total);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, h->d_total, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (n_valid) *n_valid = (int64_t)total;
+    if (!total) return TSDF_OK;
+    {
+        size_t cap_a = h->cap_stream * 3, cap_b = h->cap_stream * 5;
+        if ((rc = grow(&h->d_pos, &cap_a, (size_t)total * 3, "voxel stream positions")) ||
+            (rc = grow(&h->d_args, &cap_b, (size_t)total * 5, "voxel stream values")))
+            return rc;
+        h->cap_stream = std::min(cap_a / 3, cap_b / 5);
+    }
+    k_voxel_stream<true><<<(unsigned)n_chunks, VS_CHUNK, 0, h->stream>>>(f, v, h->d_rgb, n_vox, nullptr, h->d_chunk_offsets,
+                                                                         h->d_pos, h->d_args);
+    CUDA_TRY(cudaGetLastError());
+    return apply_device(h, nullptr, h->d_pos, h->d_args, (long long)total, nullptr);
+}
+
+extern "C" int vbt_to_dense(tsdf_buckets *h, const int64_t dim[3], float *tsdf, float *color)
+{
+    BAD_ARG(!h || !dim || !tsdf || !color, "NULL argument");
+    BAD_ARG(dim[0] <= 0 || dim[1] <= 0 || dim[2] <= 0 || dim[0] > (1 << 20) || dim[1] > (1 << 20) || dim[2] > (1 << 20),
+            "bad volume dimensions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const long long n = (long long)dim[0] * dim[1] * dim[2];
+    float *d_t = nullptr, *d_c = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_t, n * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&d_c, n * sizeof(float))) != cudaSuccess) {
+        cudaGetLastError();
+        if (d_t) cudaFree(d_t);
+        tsdf_set_error("bucket table: dense read-out of %lld voxels: %s", n, cudaGetErrorString(e));
+        return TSDF_ERR_OOM;
+    }
+    k_vbt_fill_dense<<<2048, 256, 0, h->stream>>>(d_t, d_c, n);
+    k_vbt_scatter_dense<<<2048, 256, 0, h->stream>>>(h->t, (int)dim[0], (int)dim[1], (int)dim[2], d_t, d_c);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tsdf, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(color, d_c, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_t);
+    cudaFree(d_c);
+    if (e != cudaSuccess) {
+        tsdf_set_error("bucket table: dense read-out failed: %s", cudaGetErrorString(e));
+        return TSDF_ERR_CUDA;
     }
     return TSDF_OK;
 }

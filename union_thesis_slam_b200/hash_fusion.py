@@ -30,10 +30,17 @@ class HashTable:
     """The data structure for voxel storage and retrieval: hash tables (reference hash_fusion.py:29)."""
 
     def __init__(self, vol_bounds, voxel_size, map_size=1000000, load_factor=0.75, use_gpu=False,
-                 heap_blocks=None, rank=None, world_size=None, device=None, group=None):
+                 heap_blocks=None, rank=None, world_size=None, device=None, group=None, per_voxel=False):
         """``map_size`` is the number of table slots (reference: number of buckets,
         hash_fusion.py:36).  ``heap_blocks`` (extension) bounds the number of 8^3 blocks this rank
-        can hold; default: every block of the bounded volume, capped at map_size."""
+        can hold; default: every block of the bounded volume, capped at map_size.
+
+        ``per_voxel=True`` (extension) selects the reference's own data structure for ``integrate`` /
+        ``get_volume`` as well: one entry per voxel in the 5-slot-bucket container with float64
+        running means, inserted in the reference's order, so the occupancy metrics (entries,
+        non-empty buckets, collisions, resizes) and the volumes equal the reference's exactly.  It
+        runs on the device but sequentially (the layout is order-dependent): a parity and
+        comparison mode, orders of magnitude slower than the default block map."""
         vol_bounds = np.asarray(vol_bounds)
         assert vol_bounds.shape == (3, 2), "[!] `vol_bounds` should be of shape (3, 2)."
         self._vol_bounds = vol_bounds
@@ -66,10 +73,17 @@ class HashTable:
         self._table_size = self.stats()["table_slots"]
         self._map_size = int(map_size)
         self._voxels = None  # per-voxel container with the reference's bucket layout, created on first use
+        self._per_voxel = bool(per_voxel)
+        if self._per_voxel and self.world_size != 1:
+            raise ValueError("per_voxel=True is a single-process mode")
 
     # -- hot path ------------------------------------------------------------------------------
     def integrate(self, color_im, depth_im, cam_intr, cam_pose, obs_weight=1.):
         """Integrate an RGB-D image into the hash map (reference hash_fusion.py:103-145)."""
+        if self._per_voxel:  # the reference's per-voxel loop; obs_weight is dropped like hash_fusion.py:141,145
+            self.voxel_table.integrate_frame(self._vol_dim, self._vol_origin, self._voxel_size, self._trunc_margin,
+                                             color_im, depth_im, cam_intr, cam_pose)
+            return
         im_h, im_w = depth_im.shape
         rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
         depth = np.ascontiguousarray(depth_im, dtype=np.float64)
@@ -121,6 +135,8 @@ class HashTable:
 
     def get_volume(self):
         """tsdf (default 1) and colour (default 0) volumes (reference hash_fusion.py:442-463)."""
+        if self._per_voxel:
+            return self.voxel_table.to_dense(self._vol_dim)
         t, _, c = self.get_volume_with_weight()
         return t, c
 
