@@ -60,6 +60,10 @@ def main():
     ap.add_argument("--map-size", type=int, default=2000000)
     ap.add_argument("--raw", action="store_true", help="upload the uint16 depth and convert on the device")
     ap.add_argument("--ply", default=None, help="directory for mesh.ply / pc.ply")
+    ap.add_argument("--per-voxel-frames", type=int, default=0,
+                    help="also run the first N frames through the reference's own per-voxel bucket table on the device "
+                         "(HashTable(per_voxel=True)) and print its occupancy line of hash_demo1.py:74-82")
+    ap.add_argument("--per-voxel-map-size", type=int, default=1000000)
     args = ap.parse_args()
     ids = frame_ids(args.frames)
     cam_intr = np.loadtxt(os.path.join(args.data, "camera-intrinsics.txt"), delimiter=' ')
@@ -118,6 +122,21 @@ def main():
     for name, r in report.items():
         print("%-5s %8.2f frames/s end to end | integrate %.4f s | %d voxel updates | %8.1f MB voxel state | %s"
               % (name, r["fps"], r["integrate_s"], r["updates"], r["bytes"] / 1e6, r["note"]))
+    if args.per_voxel_frames > 0:
+        print("Initializing per-voxel hash table (reference layout)...")
+        pv = hash_fusion.HashTable(vol_bnds.copy(), voxel_size=args.voxel, map_size=args.per_voxel_map_size, per_voxel=True)
+        for n, i in enumerate(ids[:args.per_voxel_frames]):
+            color_image = cv2.cvtColor(cv2.imread(os.path.join(args.data, "frame-%06d.color.jpg" % i)), cv2.COLOR_BGR2RGB)
+            cam_pose = np.loadtxt(os.path.join(args.data, "frame-%06d.pose.txt" % i))
+            tic = time.perf_counter()
+            pv.integrate(color_image, read_depth(args.data, i), cam_intr, cam_pose, obs_weight=1.)
+            occupied, collisions = pv.get_num_non_empty_bucket(), pv.get_num_collisions()
+            print("Integrate frame {} in {} seconds.".format(n + 1, round(time.perf_counter() - tic, 2)))
+            print("Frame {}: num occupied buckets: {}; load factor: {}; collisions: {}; collision rate: {}".format(
+                n + 1, occupied, pv.get_load_factor(), collisions, collisions / max(occupied, 1)))
+        report["per_voxel"] = dict(entries=pv.count_num_hash_entries(), non_empty=pv.get_num_non_empty_bucket(),
+                                   collisions=pv.get_num_collisions(), table_size=pv.voxel_table.stats()["table_size"])
+        pv.close()
     if len(maps) == 2:
         t, c = maps["grid"].get_volume()
         ht, hc = maps["hash"].get_volume()

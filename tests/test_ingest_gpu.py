@@ -44,7 +44,7 @@ def test_demo_protocol_on_fixture_frames(tmp_path, capsys):
     import fuse_sequence
     argv = sys.argv
     sys.argv = ["fuse_sequence.py", "--frames", "0-3", "--voxel", "0.04", "--map", "both", "--map-size", "65536",
-                "--ply", str(tmp_path)]
+                "--ply", str(tmp_path), "--per-voxel-frames", "2", "--per-voxel-map-size", "50000"]
     try:
         rep = fuse_sequence.main()
     finally:
@@ -53,5 +53,7 @@ def test_demo_protocol_on_fixture_frames(tmp_path, capsys):
     assert "Average FPS" in out and "tsdf equal = True, colour equal = True" in out
     assert rep["grid"]["updates"] == rep["hash"]["updates"] > 0
     assert rep["hash"]["bytes"] < rep["grid"]["bytes"]
+    # the reference's own occupancy line (hash_demo1.py:74-82) from the per-voxel container
+    assert "num occupied buckets" in out and rep["per_voxel"]["entries"] > rep["per_voxel"]["non_empty"] > 0
     for f in ("mesh_grid.ply", "pc_grid.ply", "mesh_hash.ply", "pc_hash.ply"):
         assert os.path.getsize(tmp_path / f) > 1000

@@ -251,6 +251,9 @@ class HashTable:
     def _device_volume(self, dev):
         """(tsdf, color) float32 [X,Y,Z] torch tensors on the device (union over ranks when sharded)."""
         import torch
+        if self._per_voxel:
+            t, c = self.voxel_table.to_dense(self._vol_dim)
+            return torch.from_numpy(t).to(dev), torch.from_numpy(c).to(dev)
         shape = tuple(int(d) for d in self._vol_dim)
         t = torch.empty(shape, dtype=torch.float32, device=dev)
         c = torch.empty(shape, dtype=torch.float32, device=dev)
