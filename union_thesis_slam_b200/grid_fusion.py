@@ -59,6 +59,12 @@ class TSDFVolume:
         self._local_x = np.empty(n.value, np.int64)
         _capi.check(self._lib.tsdf_grid_local_x(self._handle, None, _capi.ptr(self._local_x)))
         self._host_cache = None  # (tsdf, weight, color) host volumes, invalidated by integrate
+        # per-call scratch for the small matrices: their pointers are taken once (ctypes pointer
+        # construction costs more than the copy)
+        self._k_buf = np.zeros((3, 3), np.float64)
+        self._tinv_buf = np.zeros((4, 4), np.float64)
+        self._k_ptr = self._k_buf.ctypes.data
+        self._tinv_ptr = self._tinv_buf.ctypes.data
 
     # -- hot path ------------------------------------------------------------------------------
     def integrate(self, color_im, depth_im, cam_intr, cam_pose, obs_weight=1.):
@@ -69,11 +75,11 @@ class TSDFVolume:
         im_h, im_w = depth_im.shape
         rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
         depth = np.ascontiguousarray(depth_im, dtype=np.float64)  # float32 depth upcasts, as in the reference
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
+        self._k_buf[...] = cam_intr
         # the reference inverts the pose on the host in float64 (grid_fusion.py:265); so do we
-        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))
+        self._tinv_buf[...] = np.linalg.inv(np.asarray(cam_pose, dtype=np.float64))
         _capi.check(self._lib.tsdf_grid_integrate(
-            self._handle, _capi.ptr(rgb), _capi.ptr(depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(rgb), _capi.ptr(depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
         self._host_cache = None
 
@@ -85,20 +91,20 @@ class TSDFVolume:
         im_h, im_w = depth_raw.shape
         rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
         raw = np.ascontiguousarray(depth_raw, dtype=np.uint16)
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
-        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = np.linalg.inv(np.asarray(cam_pose, dtype=np.float64))
         _capi.check(self._lib.tsdf_grid_integrate_u16(
-            self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight), float(depth_scale), int(invalid_raw)))
         self._host_cache = None
 
     def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
         """Frame already resident in HBM (torch uint8 [H,W,3] / float64 [H,W] tensors or raw
         device pointers); ``tinv`` is the host-computed inverse pose."""
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
-        tinv = np.ascontiguousarray(tinv, dtype=np.float64)
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = tinv
         _capi.check(self._lib.tsdf_grid_integrate_device(
-            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
         self._host_cache = None
 

@@ -72,6 +72,12 @@ class HashTable:
             int(map_size), int(heap_blocks), self.device, self.rank, self.world_size, C.byref(self._handle)))
         self._table_size = self.stats()["table_slots"]
         self._map_size = int(map_size)
+        # per-call scratch for the small matrices: their pointers are taken once (ctypes pointer
+        # construction costs more than the copy)
+        self._k_buf = np.zeros((3, 3), np.float64)
+        self._tinv_buf = np.zeros((4, 4), np.float64)
+        self._k_ptr = self._k_buf.ctypes.data
+        self._tinv_ptr = self._tinv_buf.ctypes.data
         self._voxels = None  # per-voxel container with the reference's bucket layout, created on first use
         self._per_voxel = bool(per_voxel)
         if self._per_voxel and self.world_size != 1:
@@ -87,10 +93,10 @@ class HashTable:
         im_h, im_w = depth_im.shape
         rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
         depth = np.ascontiguousarray(depth_im, dtype=np.float64)
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
-        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))  # hash_fusion.py:112
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = np.linalg.inv(np.asarray(cam_pose, dtype=np.float64))  # hash_fusion.py:112
         _capi.check(self._lib.vh_integrate(
-            self._handle, _capi.ptr(rgb), _capi.ptr(depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(rgb), _capi.ptr(depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
 
     def integrate_raw(self, color_im, depth_raw, cam_intr, cam_pose, obs_weight=1., depth_scale=1000.,
@@ -101,17 +107,17 @@ class HashTable:
         im_h, im_w = depth_raw.shape
         rgb = np.ascontiguousarray(color_im, dtype=np.uint8)
         raw = np.ascontiguousarray(depth_raw, dtype=np.uint16)
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
-        tinv = np.ascontiguousarray(np.linalg.inv(np.asarray(cam_pose, dtype=np.float64)))
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = np.linalg.inv(np.asarray(cam_pose, dtype=np.float64))
         _capi.check(self._lib.vh_integrate_u16(
-            self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight), float(depth_scale), int(invalid_raw)))
 
     def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
-        K = np.ascontiguousarray(cam_intr, dtype=np.float64)
-        tinv = np.ascontiguousarray(tinv, dtype=np.float64)
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = tinv
         _capi.check(self._lib.vh_integrate_device(
-            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, _capi.ptr(K), _capi.ptr(tinv),
+            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
 
     # -- read-out ------------------------------------------------------------------------------
