@@ -272,11 +272,21 @@ int FrameIO::upload(const uint8_t *rgb, const double *depth, int npix, const uin
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
     CUDA_TRY(cudaStreamWaitEvent(pre, h2d_done[s], 0));
-    // the caller's buffers are only borrowed for the duration of the call
-    if (pinned) CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+    // the caller's pinned buffers are read by the copy engine until h2d_done: the call must not
+    // return before that (finish_upload), but the frame's kernels can be issued meanwhile
+    borrowed = pinned ? s : -1;
     cur = s;
     *d_rgb_out = d_rgb[s];
     *d_depth_out = d_depth[s];
+    return TSDF_OK;
+}
+
+int FrameIO::finish_upload()
+{
+    if (borrowed < 0) return TSDF_OK;
+    const int s = borrowed;
+    borrowed = -1;
+    CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
     return TSDF_OK;
 }
 
@@ -303,7 +313,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
     CUDA_TRY(cudaMemcpyAsync(d_rgb[s], src_rgb, (size_t)npix * 3, cudaMemcpyHostToDevice, copy));
     CUDA_TRY(cudaEventRecord(h2d_done[s], copy));
     CUDA_TRY(cudaStreamWaitEvent(pre, h2d_done[s], 0));
-    if (pinned) CUDA_TRY(cudaEventSynchronize(h2d_done[s]));
+    borrowed = pinned ? s : -1;
     launch_depth_u16(d_depth16[s], d_depth[s], npix, depth_scale, invalid_raw, pre);
     CUDA_TRY(cudaGetLastError());
     cur = s;
@@ -658,7 +668,9 @@ extern "C" int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const doubl
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = g->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
-    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+    rc = grid_run(g, d_rgb, d_depth, H, W, f, c);
+    const int rc2 = g->io.finish_upload(); // the caller's buffers are only borrowed for the duration of the call
+    return rc ? rc : rc2;
 }
 
 extern "C" int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W,
@@ -675,7 +687,9 @@ extern "C" int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const u
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = g->io.upload_u16(rgb, depth_raw, H * W, depth_scale, invalid_raw, &d_rgb, &d_depth))) return rc;
-    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+    rc = grid_run(g, d_rgb, d_depth, H, W, f, c);
+    const int rc2 = g->io.finish_upload();
+    return rc ? rc : rc2;
 }
 
 extern "C" int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W,

@@ -238,7 +238,9 @@ extern "C" int vh_integrate(tsdf_hash *h, const uint8_t *rgb, const double *dept
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = h->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
-    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+    rc = hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+    const int rc2 = h->io.finish_upload(); // the caller's buffers are only borrowed for the duration of the call
+    return rc ? rc : rc2;
 }
 
 extern "C" int vh_integrate_u16(tsdf_hash *h, const uint8_t *rgb, const uint16_t *depth_raw, int H, int W,
@@ -255,7 +257,9 @@ extern "C" int vh_integrate_u16(tsdf_hash *h, const uint8_t *rgb, const uint16_t
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = h->io.upload_u16(rgb, depth_raw, H * W, depth_scale, invalid_raw, &d_rgb, &d_depth))) return rc;
-    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+    rc = hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+    const int rc2 = h->io.finish_upload();
+    return rc ? rc : rc2;
 }
 
 extern "C" int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,

@@ -115,6 +115,7 @@ struct FrameIO {
     cudaEvent_t k_mark[3] = {nullptr, nullptr, nullptr}; // optional stage boundaries inside a frame
     int n_marks = 0;
     int next = 0, cur = -1;
+    int borrowed = -1; // upload slot whose H2D copy still reads the caller's pinned buffers
     bool timed = false;
     // Frame timing events (k_begin / k_end / side_end) cost three API calls per frame; the dense
     // handle records them only while timing or stage profiling is switched on.
@@ -129,6 +130,7 @@ struct FrameIO {
     // converted on the device to the float64 metres the rule consumes
     int upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix, double depth_scale, int invalid_raw,
                    const uint8_t **d_rgb_out, const double **d_depth_out);
+    int finish_upload(); // waits until the copy engine has left the caller's buffers (end of an integrate call)
     int ensure_cfold(int npix);
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
     // picks the frame's scratch slot, waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it,
