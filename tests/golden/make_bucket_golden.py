@@ -26,20 +26,19 @@ from oracle import bucket_oracle as bo, ref_runner  # noqa: E402
 
 BOUNDS = [[-4.22106438, 3.86798203], [-2.6663104, 2.60146141], [0., 5.76272371]]  # tests/hash_map_test.py:11
 
-# coordinate lists of tests/hash_map_test.py (test_resize_maintain_num_entries, test_add_until_full_size_10, test_add)
-COORDS_RESIZE = [[80, 56, 0], [66, 23, 1], [64, 5, 2], [77, 87, 3], [22, 55, 4], [1, 62, 5], [54, 98, 6],
-                 [17, 35, 7], [42, 86, 8], [75, 84, 9], [72, 56, 10], [68, 94, 11], [31, 18, 12], [97, 83, 13],
-                 [21, 56, 14], [16, 38, 15], [80, 46, 16], [22, 64, 17], [68, 79, 18], [98, 10, 19],
-                 [26, 31, 20], [83, 53, 21], [11, 7, 22], [92, 7, 23], [76, 81, 24], [89, 75, 25], [2, 71, 26],
-                 [82, 10, 27], [77, 58, 28], [57, 0, 29], [80, 25, 30], [43, 92, 31], [15, 26, 32], [33, 93, 33],
-                 [77, 25, 44], [82, 56, 45], [9, 44, 46], [54, 34, 47], [0, 73, 48], [81, 95, 49]]
-COORDS_FULL10 = COORDS_RESIZE[:34] + [[23, 42, 34], [97, 22, 35], [6, 88, 36], [43, 51, 37], [6, 90, 38], [54, 83, 39]]
-COORDS_ADD = [[4, 43, 0], [48, 37, 1], [37, 33, 2], [0, 42, 3], [44, 11, 4], [2, 42, 5], [40, 0, 6],
-              [22, 43, 7], [22, 15, 8], [12, 4, 9], [38, 44, 10], [24, 8, 11], [18, 9, 12], [36, 26, 13],
-              [11, 42, 14], [5, 17, 15], [3, 38, 16], [13, 12, 17], [1, 43, 18], [18, 40, 19], [22, 3, 20],
-              [28, 40, 21], [3, 8, 22], [45, 25, 23], [15, 21, 24], [26, 49, 25], [9, 20, 26], [13, 42, 27],
-              [3, 47, 28], [3, 37, 29], [33, 14, 30], [46, 44, 31], [5, 22, 32], [33, 4, 33], [20, 41, 34],
-              [23, 48, 35], [35, 48, 36], [23, 25, 37], [9, 17, 38], [6, 38, 39]]
+def reference_test_coords():
+    """The literal coordinate lists of the reference's tests/hash_map_test.py, read from that file
+    (test name -> list of [x, y, z]); they are the reference's fixtures, not ours to restate."""
+    import ast
+    path = os.path.join(ref_runner.REFERENCE_ROOT, "tests", "hash_map_test.py")
+    out = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.FunctionDef):
+            for stmt in node.body:
+                if (isinstance(stmt, ast.Assign) and len(stmt.targets) == 1 and isinstance(stmt.targets[0], ast.Name)
+                        and stmt.targets[0].id == "world_coords" and isinstance(stmt.value, ast.List) and stmt.value.elts):
+                    out[node.name] = ast.literal_eval(stmt.value)
+    return out
 
 
 def ref_layout(ht):
@@ -135,6 +134,12 @@ def main():
     A, G, R, I = bo.OP_ADD, bo.OP_GET, bo.OP_REMOVE, bo.OP_INTEGRATE
     cases = []
     # (1) the reference's own tests
+    coords = reference_test_coords()
+    COORDS_RESIZE = coords["test_resize_maintain_num_entries"]
+    COORDS_FULL10 = coords["test_add_until_full_size_10"]
+    COORDS_ADD = coords["test_add"]
+    assert len(COORDS_RESIZE) == len(COORDS_FULL10) == len(COORDS_ADD) == 40
+    assert coords["test_remove_all_entries_full_size_10"] == COORDS_ADD
     ops = [[A] + c for c in COORDS_RESIZE] + [["resize"]] + [[G] + c for c in COORDS_RESIZE]
     cases.append(run_case(hf, he, vx, "test_resize_maintain_num_entries", 10, ops))
     cases.append(run_case(hf, he, vx, "test_add_until_full_size_10", 10, [[A] + c for c in COORDS_FULL10]))
