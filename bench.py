@@ -92,6 +92,17 @@ class ClockSampler:
         return out
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def make_frames(n, width=IM_W, height=IM_H):
     from union_thesis_slam_b200 import synth
     room = synth.room_bounds(ROOM)
@@ -120,7 +131,7 @@ def cpu_port(frames, K, room, voxel, steps, warmup, stride=CPU_SHEET_STRIDE):
     sample = "every %dth x-sheet (%d of %d sheets, %.2e voxels) of the %.3g m room grid, %d frames" % (
         stride, len(xs), int(dim[0]), len(xs) * float(dim[1]) * float(dim[2]), voxel, steps)
     return dict(value=upd / dt, unit="voxel-updates/s", cores=cores, kind="port", sample=sample,
-                frames_per_s_sample=steps / dt, seconds=dt)
+                frames_per_s_sample=steps / dt, seconds=dt, cpu_model=cpu_model(), host_cpus=os.cpu_count())
 
 
 def run_reference(args):
@@ -138,7 +149,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "host_cpus")},
         "e2e": {"value": r["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": r["frames_per_s_sample"], "gpu_launches": 0,
     }
@@ -300,7 +311,7 @@ def run_b200(args):
             line["hash"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_port(frames, K, room, VOXEL, steps=4, warmup=1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "host_cpus")}
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
