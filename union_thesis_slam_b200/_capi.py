@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsdf_b200.so")
+# TSDF_B200_LIB selects another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("TSDF_B200_LIB") or os.path.join(_HERE, "libtsdf_b200.so")
 
 TSDF_OK = 0
 STATUS = {0: "TSDF_OK", -1: "TSDF_ERR_BAD_ARG", -2: "TSDF_ERR_NO_DEVICE", -3: "TSDF_ERR_CUDA",

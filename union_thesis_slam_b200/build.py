@@ -34,11 +34,12 @@ def stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not stale():
+    if not force and not stale() and "TSDF_LIB_OUT" not in os.environ:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TSDF_NVCC_EXTRA", "").split()  # e.g. -DINTEGRATE_STAGED=0 for A/B runs
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + sources()
+    out = os.environ.get("TSDF_LIB_OUT", LIB)  # variants for A/B runs are built beside the product library
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + sources()
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(os.path.join(HERE, "build.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + res.stdout)
@@ -46,7 +47,7 @@ def build(force=False, verbose=False):
         print(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (see union_thesis_slam_b200/build.log)")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

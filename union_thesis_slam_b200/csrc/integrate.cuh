@@ -37,6 +37,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                  : "memory");
 }
 
+// Measurement switches (tools/ab_variants.sh; defaults are the shipped configuration).
+//   PIXEL_EVICT_LAST=1: depth / colour pixels are loaded with an L1 evict-last hint, so the record
+//                       stream (evict-first) does not push them out of L1.
+//   QUAD_UNROLL=1:      the two quads of a column are unrolled into one instruction stream.
+#ifndef PIXEL_EVICT_LAST
+#define PIXEL_EVICT_LAST 0
+#endif
+#ifndef QUAD_UNROLL
+#define QUAD_UNROLL 0
+#endif
+__device__ __forceinline__ double load_depth_px(const double *p)
+{
+#if PIXEL_EVICT_LAST
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t load_colour_px(const uint32_t *p)
+{
+#if PIXEL_EVICT_LAST
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // Where a quad reads its record from: global memory (rec itself) or a staged copy in shared
 // memory that becomes valid when the mbarrier phase completes.
 struct Staged {
@@ -86,7 +117,7 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     double d[4];
     uint32_t nc[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) d[e] = __ldg(f.depth + pix[e]);
+    for (int e = 0; e < 4; ++e) d[e] = load_depth_px(f.depth + pix[e]);
     float4 T4 = make_float4(1.f, 1.f, 1.f, 1.f), W4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 C4 = make_uint4(0u, 0u, 0u, 0u);
     if (!PROBE) {
@@ -96,7 +127,7 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
             C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) nc[e] = __ldg(f.cfold + pix[e]);
+        for (int e = 0; e < 4; ++e) nc[e] = load_colour_px(f.cfold + pix[e]);
         if (STAGED) { // the bulk copy was started a whole brick ago; normally this does not block
             if (!st->waited) {
                 mbar_wait(st->bar, st->parity);
@@ -166,7 +197,11 @@ __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, cons
     const double cXs = __fma_rn(f.sT[1], wy, __fma_rn(f.sT[0], wx, f.sT[3]));
     const double cYs = __fma_rn(f.sT[5], wy, __fma_rn(f.sT[4], wx, f.sT[7]));
     unsigned n = 0;
+#if QUAD_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int h = 0; h < 2; ++h) {
         const int gz = gz0 + 4 * h;
         const int nvalid = v.dim_z - gz;
