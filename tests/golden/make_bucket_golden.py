@@ -169,6 +169,42 @@ def main():
             c = [int(v) for v in rng.integers(-span, span, 3)]
             ops.append([int(rng.choice([A, A, A, G, R, R])),] + c)
         cases.append(run_case(hf, he, vx, "random_seed%d_size%d" % (seed, size), size, ops))
+    # (2b) crafted collisions: chain look-ups, removal from the middle / tail / head of a chain
+    # (hash_fusion.py:350-384 cases 1b, 2a, 2b), chains passing through a neighbour's free slots
+    def colliding(size, bucket, count, start=0):
+        out, v = [], start
+        t = bo.OracleBucketTable(size)
+        while len(out) < count:
+            p = [v % 97, (v // 97) % 89, v // (97 * 89)]
+            if t.hash_function(p) == bucket:
+                out.append(p)
+            v += 1
+        return out
+    P = colliding(64, 17, 14)
+    Q = colliding(64, 18, 7)
+    ops = [[A] + p for p in P] + [[A] + q for q in Q] + [[G] + p for p in P + Q]
+    ops += [[R] + P[7], [R] + P[13], [R] + P[4], [R] + P[0], [R] + Q[5]] + [[G] + p for p in P + Q]
+    ops += [[A] + P[7], [A] + P[0], [R] + P[9], [R] + P[5], [R] + Q[0]] + [[G] + p for p in P + Q]
+    cases.append(run_case(hf, he, vx, "crafted_chain_remove_size64", 64, ops))
+    rng = np.random.default_rng(31)
+    pool = colliding(32, 5, 12) + colliding(32, 6, 8) + colliding(32, 7, 6)
+    ops = [[int(rng.choice([A, A, G, R])),] + pool[int(rng.integers(len(pool)))] for _ in range(700)]
+    cases.append(run_case(hf, he, vx, "crafted_chain_random_size32", 32, ops))
+    # (2c) a resize whose re-insertion crosses the load factor again (add_hash_entry -> double_table_size
+    # -> add_hash_entry -> double_table_size, hash_fusion.py:207-208 inside :425-436)
+    # Buckets 1..7 of a 10-bucket table hold five entries each, chosen so that both of their residues
+    # mod 20 occur early; bucket 0 holds one.  That is 8 non-empty buckets (>= 7.5), so the next insert
+    # doubles the table, and while the 36 entries are re-added the 20-bucket table reaches 15 non-empty
+    # buckets before the last of them: the re-add of the next entry doubles again, inside the first resize.
+    ops = []
+    for b in range(1, 8):
+        lo, hi = colliding(20, b, 3), colliding(20, b + 10, 2)
+        ops += [[A] + p for p in (lo[0], hi[0], lo[1], hi[1], lo[2])]
+    ops += [[A] + colliding(20, 0, 1)[0]]
+    ops += [[A, int(rng.integers(50)), int(rng.integers(50)), 1000 + i] for i in range(12)]
+    ops += [[G] + op[1:4] for op in ops[:48]]
+    cases.append(run_case(hf, he, vx, "crafted_nested_resize_size10", 10, ops))
+    assert cases[-1]["results"][36][0] >= 0 and cases[-1]["stats"]["table_size"] >= 40
     # (3) the per-voxel integrate loop on a synthetic stream (positions revisited, colours blended)
     rng = np.random.default_rng(21)
     ops = []
