@@ -1,5 +1,5 @@
 // host_common.h -- host-side plumbing shared by the dense-grid and hash-map C ABI:
-// error reporting, per-frame constants, and the double-buffered host->device frame path.
+// error reporting, per-frame constants, and the host->device frame path (FRAME_SLOTS buffers in flight).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
