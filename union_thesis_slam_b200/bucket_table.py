@@ -75,6 +75,84 @@ class HashEntry:
         return np.array_equal(self._position, position)
 
 
+class Bucket:
+    """Host-side value type of data_structures/bucket.py:7-143: a fixed list of ``bucket_size``
+    entry slots, the last one reserved for the head of the bucket's collision chain.  The device
+    container stores the same thing as five consecutive table rows; this class exists so that code
+    written against the reference's ``Bucket`` (its tests/bucket_test.py) keeps working."""
+
+    def __init__(self, bucket_size=5):
+        self._bucket_size = bucket_size
+        self._bucket_list = [None] * self._bucket_size
+
+    def get_ith_entry(self, i):
+        try:
+            return self._bucket_list[i]
+        except IndexError:
+            print("bucket.get_ith_entry: index out of range")
+
+    def set_ith_entry(self, hash_entry, i):
+        self._bucket_list[i] = hash_entry
+
+    def remove_ith_entry(self, i):
+        self._bucket_list[i] = None
+
+    def is_empty_entry(self, i):
+        return self._bucket_list[i] is None
+
+    def get_num_entry_stored(self):
+        return sum(1 for e in self._bucket_list if e is not None)
+
+    def is_full(self):
+        return self.get_num_entry_stored() == self._bucket_size
+
+    def is_full_for_alien_entries(self):
+        return all(e is not None for e in self._bucket_list[:-1])
+
+    def is_empty(self):
+        return self.get_num_entry_stored() == 0
+
+    def is_overflow(self):
+        last = self._bucket_list[-1]
+        return last is not None and not last.is_empty_offset()
+
+    def _first_free(self, upto):
+        for i in range(upto):
+            if self._bucket_list[i] is None:
+                return i
+        return -1
+
+    def add_hash_entry(self, hash_entry):
+        """Index of the slot the entry went into, -1 if the bucket is full."""
+        i = self._first_free(self._bucket_size)
+        if i >= 0:
+            self._bucket_list[i] = hash_entry
+        return i
+
+    def add_alien_hash_entry(self, hash_entry):
+        i = self._first_free(self._bucket_size - 1)  # the last slot only takes the bucket's own list head
+        if i >= 0:
+            self._bucket_list[i] = hash_entry
+        return i
+
+    def get_hash_entry(self, world_coord):
+        for entry in self._bucket_list:
+            if entry is not None and entry.match_position(world_coord):
+                return entry
+        return None
+
+    def remove_hash_entry(self, world_coord):
+        """Index of the slot that was cleared, -1 if no entry has this position."""
+        for i, entry in enumerate(self._bucket_list):
+            if entry is not None and entry.match_position(world_coord):
+                self._bucket_list[i] = None
+                return i
+        return -1
+
+    def contains(self, hash_entry):
+        return any(e is not None and e.equals(hash_entry) for e in self._bucket_list)
+
+
 def _payload(voxel):
     """(sdf, colour, weight) float64 of a Voxel; NaN sdf marks an entry stored without one."""
     if voxel is None:
