@@ -10,7 +10,7 @@
  *   - every function returns 0 (TSDF_OK) or a negative tsdf_status; tsdf_last_error() gives the
  *     text of the calling thread's last failure.  There is NO CPU fallback: without a usable CUDA
  *     device create() fails with TSDF_ERR_NO_DEVICE.
- *   - a handle is one rank's shard, bound to one CUDA device and one stream; not thread-safe.
+ *   - a handle is one rank's shard, bound to one CUDA device and its own streams; not thread-safe.
  *   - integrate() is stream-ordered and may return before the kernels finish; download / stats /
  *     sync wait.  Host frame buffers are borrowed only for the duration of the call.
  *   - frames: rgb = H*W*3 uint8 (R,G,B), depth = H*W float64 metres with 0 = invalid,
