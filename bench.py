@@ -22,6 +22,13 @@ import sys
 import tempfile
 import time
 
+if "reference" in sys.argv:
+    # --impl reference under torch.distributed.run inherits OMP_NUM_THREADS=1: the CPU arm must use
+    # every host thread (numba prange, OpenBLAS dgemm behind np.dot, OpenMP of the C port) at any N
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        os.environ.pop(_k, None)
+    os.environ["NUMBA_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -134,22 +141,88 @@ def cpu_port(frames, K, room, voxel, steps, warmup, stride=CPU_SHEET_STRIDE):
                 frames_per_s_sample=steps / dt, seconds=dt, cpu_model=cpu_model(), host_cpus=os.cpu_count())
 
 
+REF_SLABS = 8           # the reference arm integrates REF_SLABS slabs of REF_SLAB_SHEETS x-sheets each,
+REF_SLAB_SHEETS = 8     # spread evenly over the room: 8 x 8 x 1000 x 400 = 2.56e7 voxels (1/15.6 of the grid)
+
+
+def cpu_reference(frames, K, room, voxel, steps, warmup, slabs=REF_SLABS, sheets=REF_SLAB_SHEETS):
+    """Times the UNMODIFIED reference (oracle/_ref: grid_fusion.TSDFVolume, numba CPU path) on this
+    box's host cores with the protocol of grid_demo1.py:28-41,76-87 (perf_counter around every
+    integrate call) on a bounded sample of the workload: `slabs` x-slabs of the room, each built by
+    the reference's own constructor on its own bounds and fed the same frames (the reference cannot
+    hold the whole 4.0e8-voxel grid: ~138 B/voxel of host memory).  Its cost scales with
+    the voxels VISITED (every voxel of the bounds, every frame), which is why the sample is spread
+    over the room: the sample's update density then matches the whole grid's."""
+    import contextlib
+    import io
+    from oracle import build_ref
+    gf, _ = build_ref.load()
+    import numba
+    numba.set_num_threads(min(numba.config.NUMBA_NUM_THREADS, os.cpu_count() or 1))
+    room = np.asarray(room, float)
+    width = (sheets - 0.5) * voxel   # ceil() in the reference constructor makes it `sheets` sheets
+    x_lo = np.linspace(room[0, 0], room[0, 1] - width, slabs + 2)[1:-1]
+    x_lo = np.round(x_lo / (8 * voxel)) * 8 * voxel
+    vols = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for x0 in x_lo:
+            b = room.copy()
+            b[0] = (x0, x0 + width)
+            vols.append(gf.TSDFVolume(b, voxel, use_gpu=False))
+    visits = float(sum(int(np.prod(v._vol_dim)) for v in vols))
+
+    def total_w():
+        return float(sum(np.sum(v._weight_vol_cpu, dtype=np.float64) for v in vols))
+
+    for i in range(max(1, warmup)):     # the first call JIT-compiles the numba helpers
+        c, d, p = frames[i % len(frames)]
+        for v in vols:
+            v.integrate(c, d, K, p, obs_weight=1.)
+    w0 = total_w()
+    dt = 0.0
+    for i in range(steps):
+        c, d, p = frames[(max(1, warmup) + i) % len(frames)]
+        t0 = time.perf_counter()
+        for v in vols:
+            v.integrate(c, d, K, p, obs_weight=1.)
+        dt += time.perf_counter() - t0
+    upd = total_w() - w0                 # obs_weight 1: updates == increase of the weight sum
+    sample = ("%d x-slabs of %d sheets spread over the %.3g m room grid (%.2e of %.2e voxels), %d frames, "
+              "reference TSDFVolume.integrate (numba CPU path) called per slab" % (
+                  slabs, sheets, voxel, visits, float(np.prod(np.ceil((room[:, 1] - room[:, 0]) / voxel))), steps))
+    return dict(value=upd / dt, unit="voxel-updates/s", cores=int(numba.get_num_threads()), kind="reference",
+                sample=sample, frames_per_s_sample=steps / dt, seconds=dt, cpu_model=cpu_model(),
+                host_cpus=os.cpu_count(), voxel_visits_per_s=visits * steps / dt,
+                threading_layer=numba.threading_layer(), numba=numba.__version__, numpy=np.__version__)
+
+
+def reference_built():
+    try:
+        from oracle import build_ref
+        return build_ref.built()
+    except Exception:
+        return False
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path timed on this box's host cores.  The reference
-    is pure Python + numba and does not travel to the GPU box; its arithmetic is restated in
-    oracle/tsdf_oracle.c (bit-identical, tests/test_oracle_golden.py), which is what runs here."""
+    """--impl reference: the reference's own CPU path timed on this box's host cores: the unmodified
+    reference byte-compiled into oracle/_ref (oracle/build_ref.py) -- kind "reference" -- or, when
+    oracle/_ref was never built, its C/OpenMP restatement oracle/tsdf_oracle.c -- kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    room, frames, K = make_frames(min(N_FRAMES, args.warmup + args.steps))
-    r = cpu_port(frames, K, room, VOXEL, args.steps, args.warmup)
+    room, frames, K = make_frames(min(N_FRAMES, max(1, args.warmup) + args.steps))
+    if reference_built() and not args.port:
+        r = cpu_reference(frames, K, room, VOXEL, args.steps, args.warmup)
+    else:
+        r = cpu_port(frames, K, room, VOXEL, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "tsdf_voxel_updates_per_s", "value": r["value"], "unit": "voxel-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "host_cpus")},
+        "cpu_baseline": {k: v for k, v in r.items() if k not in ("seconds", "frames_per_s_sample")},
         "e2e": {"value": r["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": r["frames_per_s_sample"], "gpu_launches": 0,
     }
@@ -412,6 +485,7 @@ def _main(out):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-hash", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--port", action="store_true", help="--impl reference: time the C/OpenMP port instead of oracle/_ref")
     ap.add_argument("--workload", default="dense", choices=["dense", "hash"],
                     help="hash: print the hash-map line alone (works under torchrun: blocks sharded by owner hash)")
     args = ap.parse_args()
