@@ -1,0 +1,102 @@
+"""Long-history parity on the GPU (-m gpu): the regimes the bench's steady state runs in.
+
+The short tests stop at 10 integrations (max weight 10).  Here weights reach the hundreds, so the
+integer-weight fast path (UNIT_W), the converged-colour shortcut (needs 2*|n-o| < w+1) and, with
+a non-unit obs_weight, the two-sum exactness check are exercised against the C oracle bit for bit.
+SURVEY Appendix B rows 50..1000 describe the same regime for the full bundled sequence (max weight
+731); the fixture holds 12 of its frames, which are cycled.
+"""
+import numpy as np
+import pytest
+
+import frames
+import scenes
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+FIXTURE_FRAMES = list(range(10)) + [500, 999]
+
+
+def _state(vol):
+    t, c = vol.get_volume()
+    return t, vol._weight_vol_cpu, c
+
+
+def _assert_equal(vol, orc, what):
+    t, w, c = _state(vol)
+    assert np.array_equal(w, orc._weight_vol_cpu), "%s: weights differ in %d voxels" % (
+        what, int((w != orc._weight_vol_cpu).sum()))
+    assert np.array_equal(t, orc._tsdf_vol_cpu), "%s: tsdf differs in %d voxels (max %.3g)" % (
+        what, int((t != orc._tsdf_vol_cpu).sum()), float(np.abs(t - orc._tsdf_vol_cpu).max()))
+    assert np.array_equal(c, orc._color_vol_cpu), "%s: colour differs in %d voxels" % (
+        what, int((c != orc._color_vol_cpu).sum()))
+
+
+def test_config1_300_integrations_unit_weight():
+    """2 cm grid over the bundled bounds, the 12 fixture frames cycled for 300 integrations
+    (weights up to 250): all three planes equal the oracle at 50, 150 and 300 integrations."""
+    from union_thesis_slam_b200 import grid_fusion
+    K = frames.intrinsics()
+    fr = [frames.load_frame(i) for i in FIXTURE_FRAMES]
+    vol = grid_fusion.TSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    orc = oracle.OracleTSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    total = 0
+    for n in range(1, 301):
+        c, d, p = fr[(n - 1) % len(fr)]
+        vol.integrate(c, d, K, p, obs_weight=1.)
+        total += orc.integrate(c, d, K, p, obs_weight=1.)
+        if n in (50, 150, 300):
+            _assert_equal(vol, orc, "after %d integrations" % n)
+    assert float(orc._weight_vol_cpu.max()) >= 200.0
+    assert vol.stats()["updated_total"] == total
+
+
+@pytest.mark.parametrize("obs_cycle", [(0.5,), (2.0, 0.75, 1.0), (1.0, 1.0, 1.0, 0.3)])
+def test_config1_long_history_non_unit_weights(obs_cycle):
+    """Same frames with float32-representable (two-sum fast path) and non-representable (0.3: always the
+    IEEE slow path) observation weights for 120 integrations."""
+    from union_thesis_slam_b200 import grid_fusion
+    K = frames.intrinsics()
+    fr = [frames.load_frame(i) for i in FIXTURE_FRAMES]
+    vol = grid_fusion.TSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    orc = oracle.OracleTSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    for n in range(120):
+        c, d, p = fr[n % len(fr)]
+        obs = obs_cycle[n % len(obs_cycle)]
+        vol.integrate(c, d, K, p, obs_weight=obs)
+        orc.integrate(c, d, K, p, obs_weight=obs)
+    _assert_equal(vol, orc, "obs cycle %r" % (obs_cycle,))
+
+
+def test_bench_room_steady_state_oracle_sheets():
+    """The bench's own workload (10 x 10 x 4 m room, 1 cm, bench.py's 32-frame trajectory) for 96
+    frames -- three passes, weights up to ~90, the regime of the bench's timed region -- against the
+    oracle on every 40th x-sheet (25 sheets x 1000 x 400 voxels)."""
+    import torch
+    from union_thesis_slam_b200 import _capi, grid_fusion, synth
+    free, _ = torch.cuda.mem_get_info()
+    assert free > 12e9, "needs ~10 GB of free HBM (another process is holding memory?)"
+    room = synth.room_bounds((10.0, 10.0, 4.0))
+    fr, K = synth.room_stream(32, room, seed=0)
+    vol = grid_fusion.TSDFVolume(room.copy(), 0.01)
+    X, Y, Z = (int(d) for d in vol._vol_dim)
+    xs = np.arange(3, X, 40, dtype=np.int64)
+    orc = oracle.OracleTSDFVolume(room.copy(), 0.01, xs=xs)
+    for n in range(96):
+        c, d, p = fr[n % 32]
+        vol.integrate(c, d, K, p)
+        orc.integrate(c, d, K, p)
+    assert float(orc._weight_vol_cpu.max()) >= 40.0
+    dev = torch.device("cuda", vol.device)
+    want = (orc._tsdf_vol_cpu, orc._weight_vol_cpu, orc._color_vol_cpu)
+    for which in range(3):
+        plane = torch.empty((X, Y, Z), dtype=torch.float32, device=dev)  # 1.6 GB
+        args = [None, None, None]
+        args[which] = _capi.ptr(plane)
+        _capi.check(vol._lib.tsdf_grid_download_device(vol._handle, *args))
+        got = plane[torch.as_tensor(xs, device=dev)].cpu().numpy()
+        del plane
+        assert np.array_equal(got, want[which]), "plane %d differs on the oracle sheets (%d voxels)" % (
+            which, int((got != want[which]).sum()))
+    vol.close()

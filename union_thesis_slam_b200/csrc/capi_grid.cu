@@ -113,8 +113,8 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
         f->sT[i] = f->fx * Tinv[i];
         f->sT[4 + i] = f->fy * Tinv[4 + i];
     }
-    f->cxm = f->cx + FIX_MAGIC;
-    f->cym = f->cy + FIX_MAGIC;
+    f->cxm = f->cx + 0.5 + FIX_MAGIC;
+    f->cym = f->cy + 0.5 + FIX_MAGIC;
     f->trunc = g.trunc;
     f->neg_trunc = -g.trunc;
     f->obs = obs;
@@ -125,7 +125,7 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     f->H = H;
     f->W = W;
     f->depth = nullptr;
-    f->cfold = nullptr;
+    f->px = nullptr;
     for (int r = 0; r < 3; ++r)
         c->Tn[r] = sqrt(Tinv[4 * r] * Tinv[4 * r] + Tinv[4 * r + 1] * Tinv[4 * r + 1] + Tinv[4 * r + 2] * Tinv[4 * r + 2]) * 1.0000001;
     c->max_depth = 0.0;
@@ -167,9 +167,9 @@ int FrameIO::init()
     return TSDF_OK;
 }
 
-int FrameIO::ensure_cfold(int npix)
+int FrameIO::ensure_px(int npix)
 {
-    if (npix <= cap_pix && cfold_slot[0]) return TSDF_OK;
+    if (npix <= cap_pix && px_slot[0]) return TSDF_OK;
     return ensure(npix);
 }
 
@@ -185,19 +185,19 @@ int FrameIO::ensure(int npix)
         if (d_depth[i]) cudaFree(d_depth[i]);
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
         if (h_depth[i]) cudaFreeHost(h_depth[i]);
-        if (cfold_slot[i]) cudaFree(cfold_slot[i]);
+        if (px_slot[i]) cudaFree(px_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
         d_depth16[i] = nullptr;
-        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr; cfold_slot[i] = nullptr;
+        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr; px_slot[i] = nullptr;
     }
-    d_cfold = nullptr;
+    d_px = nullptr;
     cap_pix = 0;
     for (int i = 0; i < FRAME_SLOTS; ++i) {
         CUDA_TRY(cudaMalloc(&d_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMalloc(&d_depth[i], (size_t)npix * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMallocHost(&h_depth[i], (size_t)npix * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&cfold_slot[i], (size_t)npix * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&px_slot[i], (size_t)npix * sizeof(FramePixel)));
         CUDA_TRY(cudaMalloc(&d_depth16[i], (size_t)npix * sizeof(uint16_t)));
     }
     cap_pix = npix;
@@ -325,7 +325,7 @@ int FrameIO::upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix,
 int FrameIO::begin_kernels()
 {
     slot = (slot + 1) % FRAME_SLOTS;
-    d_cfold = cfold_slot[slot];
+    d_px = px_slot[slot];
     fs = reinterpret_cast<FrameScratch *>(scratch_slot[slot]);
     pyr = pyr_slot[slot];
     // the integrate kernels of the frame FRAME_SLOTS calls ago were the last readers of this slot
@@ -433,7 +433,7 @@ void FrameIO::release()
             if (side_int_done[k][i]) cudaEventDestroy(side_int_done[k][i]);
             if (side_slot_free[k][i]) cudaEventDestroy(side_slot_free[k][i]);
         }
-        if (cfold_slot[i]) cudaFree(cfold_slot[i]);
+        if (px_slot[i]) cudaFree(px_slot[i]);
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
         if (pre_done[i]) cudaEventDestroy(pre_done[i]);
@@ -622,17 +622,17 @@ extern "C" int tsdf_grid_destroy(tsdf_grid *g) { return grid_free(g); }
 static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
                     CullParams &c)
 {
-    int rc = g->io.ensure_cfold(H * W);
+    int rc = g->io.ensure_px(H * W);
     if (rc || (rc = g->io.ensure_tiles(H, W))) return rc;
     if ((rc = g->io.begin_kernels())) return rc;
     BrickRef *list = g->vis_list[g->io.slot];
     c.pyr = g->io.pyr;
     f.depth = d_depth;
-    f.cfold = g->io.d_cfold;
+    f.px = g->io.d_px;
     g->unit_w = g->unit_w && f.obs == 1.0;
     f.unit_w = g->unit_w ? 1 : 0;
     // preparation (stream `pre`, overlaps the previous frame's integrate kernels)
-    launch_prep_frame(d_rgb, d_depth, g->io.d_cfold, g->io.fs, g->io.pyr, H, W, g->io.pre);
+    launch_prep_frame(d_rgb, d_depth, g->io.d_px, g->io.fs, g->io.pyr, H, W, g->io.pre);
     launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list, g->class_cap,
                        g->io.fs, g->io.pre);
     // Independent classes of bricks, one kernel each on its own stream: the next kernel's CTAs take

@@ -164,7 +164,7 @@ static int check_device_error(tsdf_hash *h)
 static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
                     CullParams &c, const double Tinv[16])
 {
-    int rc = h->io.ensure_cfold(H * W);
+    int rc = h->io.ensure_px(H * W);
     if (rc || (rc = h->io.ensure_tiles(H, W))) return rc;
     const int tiles_x = h->io.pyr_slot[0].tx[0], tiles_y = h->io.pyr_slot[0].ty[0];
     WalkParams w;
@@ -198,13 +198,13 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     BrickRef *list = h->vis_list[h->io.slot];
     c.pyr = h->io.pyr;
     f.depth = d_depth;
-    f.cfold = h->io.d_cfold;
+    f.px = h->io.d_px;
     h->unit_w = h->unit_w && f.obs == 1.0;
     f.unit_w = h->unit_w ? 1 : 0;
     // allocation + compaction (stream `pre`; they only insert keys and read table state, so they
     // overlap the previous frame's integrate kernel, which only touches records / vals / the heap)
     cudaStream_t s = h->io.pre;
-    launch_prep_frame(d_rgb, d_depth, h->io.d_cfold, h->io.fs, h->io.pyr, H, W, s);
+    launch_prep_frame(d_rgb, d_depth, h->io.d_px, h->io.fs, h->io.pyr, H, W, s);
     CUDA_TRY(cudaGetLastError());
     if (h->ray_walk) {
         CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));

@@ -26,7 +26,7 @@ __global__ void k_fill_bricks(float4 *bricks, size_t n_float4)
 // grid_fusion.py:228-232 colour fold (as an exact integer), max valid depth of the frame and the
 // per-tile max-depth pyramid.  One warp per 8x8-pixel tile, two horizontally adjacent pixels per lane.
 __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__restrict__ depth,
-                             uint32_t *__restrict__ cfold, FrameScratch *fs, TilePyramid pyr, int H, int W)
+                             FramePixel *__restrict__ px, FrameScratch *fs, TilePyramid pyr, int H, int W)
 {
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -40,9 +40,13 @@ __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__re
             if (u + k < W) {
                 const int p = v * W + u + k;
                 const uint32_t r = __ldg(rgb + 3 * p), g = __ldg(rgb + 3 * p + 1), b = __ldg(rgb + 3 * p + 2);
-                cfold[p] = (b << 16) | (g << 8) | r;
                 const double d = __ldg(depth + p);
-                if (d > 0.0) m = fmaxf(m, __double2float_ru(d));
+                const bool valid = d > 0.0; // grid_fusion.py:284; false for 0, negatives and NaN
+                // one 16-byte store: {depth or -inf, folded colour, 0}
+                const double ds = valid ? d : __longlong_as_double(0xFFF0000000000000ll);
+                *reinterpret_cast<uint4 *>(px + p) = make_uint4((unsigned)__double2loint(ds), (unsigned)__double2hiint(ds),
+                                                                (b << 16) | (g << 8) | r, 0u);
+                if (valid) m = fmaxf(m, __double2float_ru(d));
             }
     }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -269,11 +273,11 @@ void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_
     k_fill_bricks<<<sm_count * 8, 256, 0, s>>>(reinterpret_cast<float4 *>(bricks), n4);
 }
 
-void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
+void launch_prep_frame(const uint8_t *rgb, const double *depth, FramePixel *px, FrameScratch *fs,
                        const TilePyramid &pyr, int H, int W, cudaStream_t s)
 {
     const int warps = pyr.tx[0] * pyr.ty[0];
-    k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, cfold, fs, pyr, H, W);
+    k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, px, fs, pyr, H, W);
 }
 
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s)

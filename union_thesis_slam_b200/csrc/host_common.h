@@ -99,13 +99,13 @@ struct FrameIO {
     uint16_t *d_depth16[FRAME_SLOTS] = {}; // raw sensor depth (frame ingest path)
     // per-frame scratch, one set per frame slot: [FrameScratch | tile pyramid levels 1..3]
     // (cleared every frame), then pyramid level 0
-    uint32_t *cfold_slot[FRAME_SLOTS] = {};
+    FramePixel *px_slot[FRAME_SLOTS] = {}; // prepared frames (depth + folded colour, 16 B per pixel)
     uint8_t *scratch_slot[FRAME_SLOTS] = {};
     TilePyramid pyr_slot[FRAME_SLOTS] = {};
     size_t clear_bytes = 0;
     int slot = FRAME_SLOTS - 1; // scratch slot of the frame being issued (advanced by begin_kernels)
     // views of the current slot (after a frame: of the last frame issued)
-    uint32_t *d_cfold = nullptr;
+    FramePixel *d_px = nullptr;
     FrameScratch *fs = nullptr;
     TilePyramid pyr{};
     int tiles_H = 0, tiles_W = 0;
@@ -131,7 +131,7 @@ struct FrameIO {
     int upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix, double depth_scale, int invalid_raw,
                    const uint8_t **d_rgb_out, const double **d_depth_out);
     int finish_upload(); // waits until the copy engine has left the caller's buffers (end of an integrate call)
-    int ensure_cfold(int npix);
+    int ensure_px(int npix);
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
     // picks the frame's scratch slot, waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it,
     // clears FrameScratch + pyramid levels 1..3

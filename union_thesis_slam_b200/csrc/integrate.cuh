@@ -47,26 +47,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #ifndef QUAD_UNROLL
 #define QUAD_UNROLL 0
 #endif
-__device__ __forceinline__ double load_depth_px(const double *p)
+// One prepared pixel (depth + folded colour) in a single 16-byte read-only load.
+__device__ __forceinline__ void load_pixel(const FramePixel *p, double &depth, uint32_t &colour)
 {
+    uint4 v;
 #if PIXEL_EVICT_LAST
-    double v;
-    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
 #else
-    return __ldg(p);
+    v = __ldg(reinterpret_cast<const uint4 *>(p));
 #endif
+    depth = __hiloint2double((int)v.y, (int)v.x);
+    colour = v.z;
 }
-__device__ __forceinline__ uint32_t load_colour_px(const uint32_t *p)
-{
-#if PIXEL_EVICT_LAST
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
+__device__ __forceinline__ double load_pixel_depth(const FramePixel *p) { return __ldg(&p->depth); }
 
 // Where a quad reads its record from: global memory (rec itself) or a staged copy in shared
 // memory that becomes valid when the mbarrier phase completes.
@@ -117,7 +112,10 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     double d[4];
     uint32_t nc[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) d[e] = load_depth_px(f.depth + pix[e]);
+    for (int e = 0; e < 4; ++e) {
+        if (PROBE) d[e] = load_pixel_depth(f.px + pix[e]);
+        else load_pixel(f.px + pix[e], d[e], nc[e]);
+    }
     float4 T4 = make_float4(1.f, 1.f, 1.f, 1.f), W4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 C4 = make_uint4(0u, 0u, 0u, 0u);
     if (!PROBE) {
@@ -126,8 +124,6 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
             W4 = __ldcs(reinterpret_cast<const float4 *>(rec + BRICK_VOX));
             C4 = __ldcs(reinterpret_cast<const uint4 *>(rec + 2 * BRICK_VOX));
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) nc[e] = load_colour_px(f.cfold + pix[e]);
         if (STAGED) { // the bulk copy was started a whole brick ago; normally this does not block
             if (!st->waited) {
                 mbar_wait(st->bar, st->parity);
@@ -144,7 +140,7 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         diff[e] = __dadd_rn(d[e], -Z[e]);
-        pass[e] = cand[e] && d[e] > 0.0 && diff[e] >= f.neg_trunc;
+        pass[e] = cand[e] && diff[e] >= f.neg_trunc; // rejected depths are stored as -inf (FramePixel)
         band[e] = diff[e] < f.trunc;
     }
     if (!(pass[0] || pass[1] || pass[2] || pass[3])) return 0;

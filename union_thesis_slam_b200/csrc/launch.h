@@ -7,6 +7,7 @@ struct FrameParams;
 struct VolumeParams;
 struct CullParams;
 struct BrickRef;
+struct FramePixel;
 
 // Reset by one cudaMemsetAsync at the start of every frame.
 struct FrameScratch {
@@ -53,7 +54,7 @@ struct Totals {
 };
 
 void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_t s);
-void launch_prep_frame(const uint8_t *rgb, const double *depth, uint32_t *cfold, FrameScratch *fs,
+void launch_prep_frame(const uint8_t *rgb, const double *depth, FramePixel *px, FrameScratch *fs,
                        const TilePyramid &pyr, int H, int W, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         int classes, BrickRef *lists, size_t class_cap, FrameScratch *fs, cudaStream_t s);
