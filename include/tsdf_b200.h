@@ -105,6 +105,16 @@ int tsdf_grid_stream(tsdf_grid *g, void **stream);
  * host does not block -- for every kernel issued so far, so that an event recorded on it
  * afterwards marks the completion of all of them.  Read-out calls and sync() do this themselves. */
 int tsdf_grid_flush(tsdf_grid *g);
+/* Temporal blocking.  The reference applies one frame per integrate call (grid_fusion.py:214); its
+ * per-voxel rule has no cross-voxel term, so applying the frames k, k+1, ... to a voxel back to back
+ * gives the same bits as applying them volume by volume.  With frames > 1 (max 4) every integrate
+ * call prepares its frame at once but the volume update is deferred until `frames` calls have
+ * accumulated; then each visible brick is read once, updated by all of them in call order, and
+ * written once.  stats / download / sync / flush apply whatever is pending first, so results are
+ * always those of the calls made so far.  While frames > 1, stats' counters[0] and [2] describe the
+ * last batch issued, and device buffers passed to integrate_device are consumed before the call's
+ * successor work on the handle's streams, exactly as with frames == 1.  Default 1. */
+int tsdf_grid_set_batch(tsdf_grid *g, int frames);
 
 /* ---------------------------------------------------------------------------------------------
  * Voxel-block hash map.  Replaces hash_fusion.HashTable (hash_fusion.py:29-507) on the

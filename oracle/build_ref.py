@@ -2,7 +2,8 @@
 
 TEST / MEASUREMENT INFRASTRUCTURE ONLY.  The reference (DiWu9/Union-Thesis-SLAM) is pure Python +
 numba, so "compiling it from its own sources" means ``py_compile``: every module of the hot path
-is compiled from /root/reference into a sourceless ``.pyc`` under ``oracle/_ref/`` -- no reference
+is compiled from /root/reference into sourceless bytecode (``<module>.refbin``: the ``.pyc`` image under a
+suffix that file-sync tools do not drop as a cache file) under ``oracle/_ref/`` -- no reference
 source text enters this repository, and ``oracle/_ref/`` is git-ignored (it is NOT gpurun-ignored,
 so it travels to the GPU box like our own built ``.so`` files).  numba JIT-compiles from bytecode,
 so the sourceless modules run the reference's numba CPU path unchanged (grid_fusion.py:170-212,
@@ -15,6 +16,7 @@ and by tests that cross-check the C oracle against the reference.  Never by the 
     python -m oracle.build_ref        # needs /root/reference; no-op with a note when it is absent
 """
 import importlib.util
+import marshal
 import os
 import py_compile
 import sys
@@ -31,8 +33,15 @@ def source_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "grid_fusion.py"))
 
 
+SUFFIX = ".refbin"
+
+
+def _out(rel):
+    return os.path.join(REF_OUT, rel[:-3] + SUFFIX)
+
+
 def built():
-    return all(os.path.isfile(os.path.join(REF_OUT, m + "c")) for m in MODULES)
+    return all(os.path.isfile(_out(m)) for m in MODULES)
 
 
 def build(force=False):
@@ -42,11 +51,11 @@ def build(force=False):
         return REF_OUT if built() else None
     for rel in MODULES:
         src = os.path.join(REFERENCE_ROOT, rel)
-        dst = os.path.join(REF_OUT, rel + "c")
+        dst = _out(rel)
         if not force and os.path.isfile(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        # dfile: the path shown in tracebacks; sourceless import needs the .pyc beside where the .py would be
+        # dfile: the path shown in tracebacks
         py_compile.compile(src, cfile=dst, dfile="reference/" + rel, doraise=True, optimize=0)
     with open(os.path.join(REF_OUT, "BUILD_INFO.txt"), "w") as fh:
         fh.write("byte-compiled from %s by oracle/build_ref.py with Python %s (magic %s)\n" % (
@@ -66,12 +75,34 @@ def load():
         sk.measure = types.ModuleType("skimage.measure")
         sys.modules["skimage"] = sk
         sys.modules["skimage.measure"] = sk.measure
-    if REF_OUT not in sys.path:
-        sys.path.insert(0, REF_OUT)
-    import grid_fusion  # noqa: E402  (the reference's module name)
-    import hash_fusion  # noqa: E402
-    if not grid_fusion.__file__.startswith(REF_OUT):
-        raise RuntimeError("grid_fusion resolved to %s, not to oracle/_ref" % grid_fusion.__file__)
+    magic = importlib.util.MAGIC_NUMBER
+
+    def load_module(name, rel, package=None):
+        if name in sys.modules and getattr(sys.modules[name], "__file__", "").startswith(REF_OUT):
+            return sys.modules[name]
+        path = _out(rel)
+        with open(path, "rb") as fh:
+            data = fh.read()
+        if data[:4] != magic:
+            raise RuntimeError("%s was byte-compiled by another Python (magic %s, this interpreter %s): rebuild "
+                               "oracle/_ref" % (path, data[:4].hex(), magic.hex()))
+        mod = types.ModuleType(name)
+        mod.__file__ = path
+        mod.__package__ = package or ""
+        sys.modules[name] = mod
+        exec(marshal.loads(data[16:]), mod.__dict__)  # the module body, exactly what `import` would run
+        return mod
+
+    pkg = sys.modules.get("data_structures")
+    if pkg is None or not getattr(pkg, "__file__", "").startswith(REF_OUT):
+        pkg = types.ModuleType("data_structures")
+        pkg.__file__ = os.path.join(REF_OUT, "data_structures")
+        pkg.__path__ = []
+        sys.modules["data_structures"] = pkg
+    for sub in ("voxel", "hash_entry", "bucket"):  # dependency order of the reference's own imports
+        setattr(pkg, sub, load_module("data_structures." + sub, "data_structures/%s.py" % sub, "data_structures"))
+    grid_fusion = load_module("grid_fusion", "grid_fusion.py")
+    hash_fusion = load_module("hash_fusion", "hash_fusion.py")
     return grid_fusion, hash_fusion
 
 

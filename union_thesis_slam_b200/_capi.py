@@ -38,6 +38,7 @@ SYMBOLS = [
     ("tsdf_grid_last_stage_ms", _i, [_p, _p, _p]),
     ("tsdf_grid_stream", _i, [_p, _pp]),
     ("tsdf_grid_flush", _i, [_p]),
+    ("tsdf_grid_set_batch", _i, [_p, _i]),
     ("vh_create", _i, [_p, _p, _d, _d, _i64, _i64, _i, _i, _i, _pp]),
     ("vh_destroy", _i, [_p]),
     ("vh_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),

@@ -124,6 +124,7 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     f->unit_w = 0; // set by the handle, which knows the history of obs_weight
     f->H = H;
     f->W = W;
+    f->npix = H * W;
     f->depth = nullptr;
     f->px = nullptr;
     for (int r = 0; r < 3; ++r)
@@ -185,10 +186,13 @@ int FrameIO::ensure(int npix)
         if (d_depth[i]) cudaFree(d_depth[i]);
         if (h_rgb[i]) cudaFreeHost(h_rgb[i]);
         if (h_depth[i]) cudaFreeHost(h_depth[i]);
-        if (px_slot[i]) cudaFree(px_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
         d_depth16[i] = nullptr;
-        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr; px_slot[i] = nullptr;
+        d_rgb[i] = nullptr; d_depth[i] = nullptr; h_rgb[i] = nullptr; h_depth[i] = nullptr;
+    }
+    for (int i = 0; i < MAX_PREP; ++i) {
+        if (px_slot[i]) cudaFree(px_slot[i]);
+        px_slot[i] = nullptr;
     }
     d_px = nullptr;
     cap_pix = 0;
@@ -197,10 +201,43 @@ int FrameIO::ensure(int npix)
         CUDA_TRY(cudaMalloc(&d_depth[i], (size_t)npix * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&h_rgb[i], (size_t)npix * 3));
         CUDA_TRY(cudaMallocHost(&h_depth[i], (size_t)npix * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&px_slot[i], (size_t)npix * sizeof(FramePixel)));
         CUDA_TRY(cudaMalloc(&d_depth16[i], (size_t)npix * sizeof(uint16_t)));
     }
+    for (int i = 0; i < FRAME_SLOTS * subs; ++i) CUDA_TRY(cudaMalloc(&px_slot[i], ((size_t)npix + 1) * sizeof(FramePixel)));
     cap_pix = npix;
+    return TSDF_OK;
+}
+
+int FrameIO::set_subs(int n)
+{
+    if (n <= subs) return TSDF_OK;
+    // more prepared frames per slot: drain everything and let ensure()/ensure_tiles() reallocate
+    CUDA_TRY(cudaStreamSynchronize(pre));
+    CUDA_TRY(cudaStreamSynchronize(compute));
+    { int rc_ = sync_side(); if (rc_) return rc_; }
+    CUDA_TRY(cudaStreamSynchronize(copy));
+    subs = n;
+    const int npix = cap_pix;
+    if (npix > 0) {
+        for (int i = 0; i < FRAME_SLOTS * subs; ++i)
+            if (!px_slot[i]) CUDA_TRY(cudaMalloc(&px_slot[i], ((size_t)npix + 1) * sizeof(FramePixel)));
+    }
+    tiles_H = tiles_W = 0; // scratch is reallocated for all subs by the next ensure_tiles()
+    return TSDF_OK;
+}
+
+int FrameIO::clear_sub(int sub)
+{
+    CUDA_TRY(cudaMemsetAsync(scratch_slot[prep_index(slot, sub)], 0, clear_bytes, pre));
+    return TSDF_OK;
+}
+
+int FrameIO::release_upload_after_prep()
+{
+    if (cur >= 0) {
+        CUDA_TRY(cudaEventRecord(slot_free[cur], pre));
+        cur = -1;
+    }
     return TSDF_OK;
 }
 
@@ -223,9 +260,11 @@ int FrameIO::ensure_tiles(int H, int W)
     p.ty[0] = (H + 7) / 8;
     off[0] = total;
     total += (size_t)p.tx[0] * p.ty[0] * sizeof(float);
-    for (int i = 0; i < FRAME_SLOTS; ++i) {
+    for (int i = 0; i < MAX_PREP; ++i) {
         if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         scratch_slot[i] = nullptr;
+    }
+    for (int i = 0; i < FRAME_SLOTS * subs; ++i) {
         CUDA_TRY(cudaMalloc(&scratch_slot[i], total));
         CUDA_TRY(cudaMemset(scratch_slot[i], 0, total));
         pyr_slot[i] = p;
@@ -433,8 +472,6 @@ void FrameIO::release()
             if (side_int_done[k][i]) cudaEventDestroy(side_int_done[k][i]);
             if (side_slot_free[k][i]) cudaEventDestroy(side_slot_free[k][i]);
         }
-        if (px_slot[i]) cudaFree(px_slot[i]);
-        if (scratch_slot[i]) cudaFree(scratch_slot[i]);
         if (d_depth16[i]) cudaFree(d_depth16[i]);
         if (pre_done[i]) cudaEventDestroy(pre_done[i]);
         if (int_done[i]) cudaEventDestroy(int_done[i]);
@@ -444,6 +481,10 @@ void FrameIO::release()
         if (h_depth[i]) cudaFreeHost(h_depth[i]);
         if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
         if (slot_free[i]) cudaEventDestroy(slot_free[i]);
+    }
+    for (int i = 0; i < MAX_PREP; ++i) {
+        if (px_slot[i]) cudaFree(px_slot[i]);
+        if (scratch_slot[i]) cudaFree(scratch_slot[i]);
     }
     for (int i = 0; i < 3; ++i)
         if (k_mark[i]) cudaEventDestroy(k_mark[i]);
@@ -530,12 +571,22 @@ struct tsdf_grid {
     CounterStore counters;
     bool profile_stages = false;
     bool unit_w = true; // every frame so far had obs_weight == 1 (weights are integers)
+    // Temporal blocking: up to `batch` consecutive frames are prepared as they arrive and applied to
+    // every brick in ONE visit (tsdf_grid_set_batch).  q_* is the batch being collected.
+    int batch = 1;
+    int q_n = 0;
+    FrameParams q_f[DENSE_MAX_BATCH];
+    CullParams q_c[DENSE_MAX_BATCH];
+    FrameScratch *q_fs[DENSE_MAX_BATCH] = {};
 };
+
+static int grid_flush_batch(tsdf_grid *g);
 
 static int grid_free(tsdf_grid *g)
 {
     if (!g) return TSDF_OK;
     cudaSetDevice(g->device);
+    if (g->bricks && g->q_n) grid_flush_batch(g); // frames still waiting for their batch are applied, not dropped
     g->io.release();
     g->geom.release();
     if (g->bricks) cudaFree(g->bricks);
@@ -619,24 +670,22 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
 
 extern "C" int tsdf_grid_destroy(tsdf_grid *g) { return grid_free(g); }
 
-static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
-                    CullParams &c)
+// Issues cull + integrate for the frames collected so far (no-op when none are pending).
+static int grid_flush_batch(tsdf_grid *g)
 {
-    int rc = g->io.ensure_px(H * W);
-    if (rc || (rc = g->io.ensure_tiles(H, W))) return rc;
-    if ((rc = g->io.begin_kernels())) return rc;
+    const int k = g->q_n;
+    if (!k) return TSDF_OK;
+    g->q_n = 0;
+    int rc;
     BrickRef *list = g->vis_list[g->io.slot];
-    c.pyr = g->io.pyr;
-    f.depth = d_depth;
-    f.px = g->io.d_px;
-    g->unit_w = g->unit_w && f.obs == 1.0;
-    f.unit_w = g->unit_w ? 1 : 0;
-    // preparation (stream `pre`, overlaps the previous frame's integrate kernels)
-    launch_prep_frame(d_rgb, d_depth, g->io.d_px, g->io.fs, g->io.pyr, H, W, g->io.pre);
-    launch_cull_bricks(f, c, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list, g->class_cap,
-                       g->io.fs, g->io.pre);
+    if (k == 1)
+        launch_cull_bricks(g->q_f[0], g->q_c[0], g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world, g->classes, list,
+                           g->class_cap, g->q_fs[0], g->io.pre);
+    else
+        launch_cull_bricks_batch(g->q_f, g->q_c, g->q_fs, k, g->nlbx, g->geom.nb[1], g->geom.nb[2], g->rank, g->world,
+                                 g->classes, list, g->class_cap, g->io.pre);
     // Independent classes of bricks, one kernel each on its own stream: the next kernel's CTAs take
-    // the SM slots a kernel's tail frees, and the next frame's first kernel does the same for the
+    // the SM slots a kernel's tail frees, and the next batch's first kernel does the same for the
     // last one, so neither the launch gap nor the drain of the persistent grids leaves the SMs idle.
     // With stage profiling on, all run on `compute` so that the stage marks delimit them.
     g->io.n_side = g->profile_stages ? 0 : g->classes - 1;
@@ -645,14 +694,50 @@ static int grid_run(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, i
     if (g->profile_stages && (rc = g->io.mark())) return rc;
     const VolumeParams vp = g->geom.params();
     const int warps = g->integrate_grid * (INTEGRATE_THREADS / 32);
-    for (int k = 0; k < g->classes; ++k) {
-        const int *count = k ? &g->io.fs->vis_extra[k - 1] : &g->io.fs->vis_count;
-        launch_integrate_dense(f, vp, list + k * g->class_cap, count, g->bricks, g->counters.view(g->io.slot, k * warps),
-                               g->integrate_grid, (k && g->io.n_side) ? g->io.side[k - 1] : g->io.compute);
+    for (int c = 0; c < g->classes; ++c) {
+        const int *count = c ? &g->q_fs[0]->vis_extra[c - 1] : &g->q_fs[0]->vis_count;
+        cudaStream_t st = (c && g->io.n_side) ? g->io.side[c - 1] : g->io.compute;
+        if (k == 1)
+            launch_integrate_dense(g->q_f[0], vp, list + c * g->class_cap, count, g->bricks,
+                                   g->counters.view(g->io.slot, c * warps), g->integrate_grid, st);
+        else
+            launch_integrate_dense_batch(g->q_f, k, vp, list + c * g->class_cap, count, g->bricks,
+                                         g->counters.view(g->io.slot, c * warps), g->integrate_grid, st);
     }
     CUDA_TRY(cudaGetLastError());
-    if ((rc = g->io.end_kernels())) return rc;
+    return g->io.end_kernels();
+}
+
+// Prepares one frame (stream `pre`, overlaps the previous batch's integrate kernels) and adds it to
+// the batch being collected; a full batch is issued at once.
+static int grid_enqueue(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W, FrameParams &f,
+                        CullParams &c)
+{
+    int rc;
+    // one image size per batch (a new size reallocates the per-frame scratch: nothing may be pending)
+    if (g->q_n && (g->q_f[0].H != H || g->q_f[0].W != W) && (rc = grid_flush_batch(g))) return rc;
+    if ((rc = g->io.ensure_px(H * W)) || (rc = g->io.ensure_tiles(H, W))) return rc;
+    const int sub = g->q_n;
+    if (sub == 0) {
+        if ((rc = g->io.begin_kernels())) return rc; // picks the slot, waits for its previous user, clears sub 0
+    } else if ((rc = g->io.clear_sub(sub)))
+        return rc;
+    const int pi = FrameIO::prep_index(g->io.slot, sub);
+    FrameScratch *fs = reinterpret_cast<FrameScratch *>(g->io.scratch_slot[pi]);
+    c.pyr = g->io.pyr_slot[pi];
+    f.depth = d_depth;
+    f.px = g->io.px_slot[pi];
+    g->unit_w = g->unit_w && f.obs == 1.0;
+    f.unit_w = g->unit_w ? 1 : 0;
+    launch_prep_frame(d_rgb, d_depth, g->io.px_slot[pi], fs, g->io.pyr_slot[pi], H, W, g->io.pre);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = g->io.release_upload_after_prep())) return rc;
+    g->q_f[sub] = f;
+    g->q_c[sub] = c;
+    g->q_fs[sub] = fs;
+    g->q_n = sub + 1;
     g->frames++;
+    if (g->q_n >= g->batch) return grid_flush_batch(g);
     return TSDF_OK;
 }
 
@@ -668,7 +753,7 @@ extern "C" int tsdf_grid_integrate(tsdf_grid *g, const uint8_t *rgb, const doubl
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = g->io.upload(rgb, depth, H * W, &d_rgb, &d_depth))) return rc;
-    rc = grid_run(g, d_rgb, d_depth, H, W, f, c);
+    rc = grid_enqueue(g, d_rgb, d_depth, H, W, f, c);
     const int rc2 = g->io.finish_upload(); // the caller's buffers are only borrowed for the duration of the call
     return rc ? rc : rc2;
 }
@@ -687,7 +772,7 @@ extern "C" int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const u
     const uint8_t *d_rgb;
     const double *d_depth;
     if ((rc = g->io.upload_u16(rgb, depth_raw, H * W, depth_scale, invalid_raw, &d_rgb, &d_depth))) return rc;
-    rc = grid_run(g, d_rgb, d_depth, H, W, f, c);
+    rc = grid_enqueue(g, d_rgb, d_depth, H, W, f, c);
     const int rc2 = g->io.finish_upload();
     return rc ? rc : rc2;
 }
@@ -701,7 +786,7 @@ extern "C" int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, co
     CullParams c;
     int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
     if (rc) return rc;
-    return grid_run(g, d_rgb, d_depth, H, W, f, c);
+    return grid_enqueue(g, d_rgb, d_depth, H, W, f, c);
 }
 
 extern "C" int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs)
@@ -722,8 +807,8 @@ extern "C" int tsdf_grid_download_device(tsdf_grid *g, float *d_tsdf, float *d_w
 {
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
-    int rc = g->io.join();
-    if (rc) return rc;
+    int rc = grid_flush_batch(g);
+    if (rc || (rc = g->io.join())) return rc;
     launch_unbrick(g->bricks, (int)g->n_x_local, (int)g->geom.dim[1], (int)g->geom.dim[2], g->geom.nb[1],
                    g->geom.nb[2], d_tsdf, d_weight, d_color, g->sm_count, g->io.compute);
     CUDA_TRY(cudaGetLastError());
@@ -737,8 +822,8 @@ extern "C" int tsdf_grid_download(tsdf_grid *g, float *tsdf, float *weight, floa
     CUDA_TRY(cudaSetDevice(g->device));
     const size_t n = (size_t)g->n_x_local * g->geom.dim[1] * g->geom.dim[2];
     if (!n) return TSDF_OK;
-    int rc = g->io.join();
-    if (rc) return rc;
+    int rc = grid_flush_batch(g);
+    if (rc || (rc = g->io.join())) return rc;
     // one plane at a time keeps the device-side scratch at 4 B/voxel
     float *scratch = nullptr;
     CUDA_TRY(cudaMalloc(&scratch, n * sizeof(float)));
@@ -765,9 +850,9 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
     BAD_ARG(!g || !counters, "NULL argument");
     CUDA_TRY(cudaSetDevice(g->device));
     const StatsBlock *st = nullptr;
+    int rc = grid_flush_batch(g);
+    if (rc || (rc = g->io.join())) return rc;
     const int slot = g->frames > 0 ? g->io.slot : 0;
-    int rc = g->io.join();
-    if (rc) return rc;
     rc = g->counters.collect(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, &st);
     if (rc) return rc;
     counters[0] = g->frames > 0 ? (int64_t)st->updated_last : 0;
@@ -781,6 +866,7 @@ extern "C" int tsdf_grid_sync(tsdf_grid *g)
 {
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
+    { int rc_ = grid_flush_batch(g); if (rc_) return rc_; }
     CUDA_TRY(cudaStreamSynchronize(g->io.copy));
     CUDA_TRY(cudaStreamSynchronize(g->io.pre));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));
@@ -791,7 +877,19 @@ extern "C" int tsdf_grid_flush(tsdf_grid *g)
 {
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
-    return g->io.join();
+    int rc = grid_flush_batch(g);
+    return rc ? rc : g->io.join();
+}
+
+extern "C" int tsdf_grid_set_batch(tsdf_grid *g, int frames)
+{
+    BAD_ARG(!g, "NULL handle");
+    BAD_ARG(frames < 1 || frames > DENSE_MAX_BATCH, "batch of %d frames unsupported (1..%d)", frames, DENSE_MAX_BATCH);
+    CUDA_TRY(cudaSetDevice(g->device));
+    int rc = grid_flush_batch(g);
+    if (rc || (rc = g->io.set_subs(frames))) return rc;
+    g->batch = frames;
+    return TSDF_OK;
 }
 
 extern "C" int tsdf_grid_last_kernel_ms(tsdf_grid *g, float *ms)

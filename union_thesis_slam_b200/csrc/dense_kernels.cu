@@ -9,6 +9,9 @@
 //
 // Per frame:  prep_frame (fold colour, max depth)  ->  cull_bricks (frustum + depth range,
 // warp-aggregated compaction)  ->  integrate_bricks (persistent CTAs over the visible list).
+#include <stdlib.h>
+#include <string.h>
+
 #include "launch.h"
 #include "integrate.cuh"
 
@@ -31,6 +34,8 @@ __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__re
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= pyr.tx[0] * pyr.ty[0]) return;
+    if (tile == 0 && lane == 0) // sentinel pixel behind the image: what a voxel that projects nowhere reads
+        *reinterpret_cast<uint4 *>(px + (size_t)H * W) = make_uint4(0u, 0xFFF00000u, 0u, 0u);
     const int tx = tile % pyr.tx[0], ty = tile / pyr.tx[0];
     const int v = ty * 8 + (lane >> 2), u = tx * 8 + (lane & 3) * 2;
     float m = 0.0f;
@@ -113,66 +118,186 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
     }
 }
 
-// Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
-// (x = t>>3, y = t&7): two float4 (= one 32 B sector) per plane, read with streaming loads right
-// after the depth pixels are requested and written back straight from registers with streaming
-// stores.  One launch per class of bricks (see k_cull_bricks); `count` is that class's list length.
-// -DINTEGRATE_STAGED=1 builds the measured-and-rejected variant instead (profiles/r1_dense_ab.txt):
-// records double-buffered through shared memory by one thread's 6 KB bulk copy (cp.async.bulk +
-// mbarrier, the TMA path) of brick i+1 while brick i is integrated.
-#ifndef INTEGRATE_L2_PREFETCH
-#define INTEGRATE_L2_PREFETCH 0
-#endif
-#ifndef INTEGRATE_STAGED
-#define INTEGRATE_STAGED 0 // measured: 0.63 vs 0.59 of the HBM roofline on the 1 cm room (profiles/)
-#endif
-#if INTEGRATE_STAGED
-template <bool UNIT_W>
-__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
-k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
-                  float *__restrict__ bricks, UpdateCounters uc)
+// Batch culling: the same test against every frame of a batch; a brick is listed once, with the mask
+// of the frames that can touch it in the top byte of bz (the integrate kernel skips the others).
+// Per-frame max depth comes from each frame's own FrameScratch; the list counters live in frame 0's.
+struct CullBatch {
+    FrameParams f[DENSE_MAX_BATCH];
+    CullParams c[DENSE_MAX_BATCH];
+    const FrameScratch *fs[DENSE_MAX_BATCH];
+    int n;
+};
+
+__global__ void k_cull_bricks_batch(CullBatch cb, int nlbx, int nby, int nbz, int rank, int world, int classes,
+                                    BrickRef *__restrict__ lists, size_t class_cap, FrameScratch *fs0)
 {
-    __shared__ __align__(128) float s_rec[2][BRICK_FLOATS];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    const int n = nlbx * nby * nbz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned mask = 0;
+    int bx = 0, by = 0, bz = 0, cls = 0;
+    if (i < n) {
+        bz = i % nbz;
+        by = (i / nbz) % nby;
+        const int lbx = i / (nbz * nby);
+        bx = lbx * world + rank;
+        cls = (lbx + by + bz) % classes;
+#pragma unroll 1
+        for (int k = 0; k < cb.n; ++k) {
+            CullParams c = cb.c[k];
+            c.max_depth = (double)__uint_as_float(cb.fs[k]->max_depth_bits);
+            if (c.max_depth > 0.0 && brick_visible(cb.f[k], c, bx, by, bz)) mask |= 1u << k;
+        }
+    }
+    const bool vis = mask != 0;
+    if (!__ballot_sync(0xffffffffu, vis)) return;
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < classes; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, vis && cls == k);
+        if (!m) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(dense_count(fs0, k), __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (vis && cls == k) {
+            BrickRef r;
+            r.bx = bx; r.by = by; r.bz = bz | (int)(mask << 24); r.storage = (uint32_t)i;
+            lists[(size_t)k * class_cap + base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
+    }
+}
+
+// Persistent CTAs of two warps; one brick per iteration, thread t owns the z-column
+// (x = t>>3, y = t&7): two quads of four voxels, i.e. two float4 (= one 32 B sector) per plane.
+// One launch per class of bricks (see k_cull_bricks); `count` is that class's list length.
+//
+// k_integrate_dense<UNIT_W, K>: K frames are applied to a brick during ONE visit (temporal blocking;
+// K = 1 is the plain per-frame kernel).  A list entry carries, in the top byte of bz, the mask of
+// the batch's frames that can touch the brick; every voxel applies them in frame order, so the
+// result is bit-identical to K single-frame launches (the rule has no cross-voxel term).  The
+// record quads are staged in thread-private shared-memory slots by cp.async one quad ahead of use
+// (integrate.cuh): the record's DRAM latency hides behind the previous quad's geometry, and between
+// the frames of a visit the record lives in the slot instead of going back to HBM.
+//
+// k_integrate_dense_v1: the round-1 kernel (record requested with the pixels, straight from global
+// memory), kept behind TSDF_DENSE_V1=1 for A/B measurements.
+#ifndef DENSE_UNROLL_FRAMES
+#define DENSE_UNROLL_FRAMES 0
+#endif
+template <int K>
+struct FrameBatch {
+    FrameParams f[K];
+};
+
+#ifndef DENSE_BATCH_MIN_CTAS
+#define DENSE_BATCH_MIN_CTAS 12 // K > 1: 80 registers (the frame loop carries more state; 64 spills ~200 B)
+#endif
+#ifndef DENSE_SM_CONTIGUOUS
+#define DENSE_SM_CONTIGUOUS 1
+#endif
+
+// Which list entry a persistent CTA takes in round r.  CTAs are dealt to SMs round-robin
+// (CTA i -> SM i % n_sm for the resident wave), so with DENSE_SM_CONTIGUOUS the CTAs that share an SM
+// -- and its L1 -- take CONSECUTIVE list entries: neighbouring bricks, whose pixel footprints and
+// lattice rows overlap.  Any placement is correct; the mapping is a permutation of each round.
+__device__ __forceinline__ int entry_of(int round, int n_sm)
+{
+#if DENSE_SM_CONTIGUOUS
+    const int per_sm = gridDim.x / n_sm; // the launcher sizes the grid as a multiple of the SM count
+    const int sm = blockIdx.x % n_sm, j = blockIdx.x / n_sm;
+    return round * (int)gridDim.x + sm * per_sm + j;
+#else
+    return round * (int)gridDim.x + blockIdx.x;
+#endif
+}
+
+template <bool UNIT_W, int K>
+__global__ void __launch_bounds__(INTEGRATE_THREADS, K == 1 ? INTEGRATE_MIN_CTAS : DENSE_BATCH_MIN_CTAS)
+k_integrate_dense(FrameBatch<K> fb, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
+                  float *__restrict__ bricks, UpdateCounters uc, int n_sm)
+{
+    // one quad record per thread: [plane][thread] float4, filled by the thread's own cp.async
+    __shared__ __align__(16) float4 s_rec[3][INTEGRATE_THREADS];
+    __shared__ unsigned s_updates[INTEGRATE_THREADS];
     const int n = *count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
-    if (t == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    unsigned my_updates = 0;
-    int b = blockIdx.x;
-    int4 br_next = make_int4(0, 0, 0, 0);
+    s_updates[t] = 0; // only this thread touches its counter: no barrier needed
+    float4 *slot = &s_rec[0][t];
+    int round = 0;
+    int b = entry_of(0, n_sm);
+    int4 br = make_int4(0, 0, 0, 0);
+    bool inb_next = false;
+    float *rec_next = nullptr;
     if (b < n) {
-        br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
-        if (t == 0) bulk_load_record(s_rec[0], bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS, &s_bar[0]);
+        br = __ldg(reinterpret_cast<const int4 *>(list) + b);
+        inb_next = br.x * BRICK + lx < v.dim_x && br.y * BRICK + ly < v.dim_y;
+        rec_next = bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t;
+        if (inb_next) prefetch_quad(slot, rec_next);
     }
-    uint32_t it = 0;
-    for (; b < n; b += gridDim.x, ++it) {
-        const int4 br = br_next;
-        const uint32_t cur = it & 1u;
-        // everyone is done reading the other buffer (it held brick it-1): refill it with brick it+1
-        __syncthreads();
-        if (b + (int)gridDim.x < n) {
-            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
-            if (t == 0)
-                bulk_load_record(s_rec[cur ^ 1u], bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS, &s_bar[cur ^ 1u]);
+    prefetch_commit();
+    while (b < n) {
+        const int4 cur = br;
+        const bool inb = inb_next;
+        float *rec = rec_next;
+        const int b_next = entry_of(++round, n_sm);
+        inb_next = false;
+        if (b_next < n) {
+            br = __ldg(reinterpret_cast<const int4 *>(list) + b_next);
+            inb_next = br.x * BRICK + lx < v.dim_x && br.y * BRICK + ly < v.dim_y;
+            rec_next = bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t;
         }
-        Staged st;
-        st.smem = s_rec[cur] + 8 * t;
-        st.bar = &s_bar[cur];
-        st.parity = (it >> 1) & 1u;
-        st.waited = false;
-        const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
-        if (gx < v.dim_x && gy < v.dim_y)
-            my_updates += integrate_column8<UNIT_W, false, true>(f, v, gx, gy, br.z * BRICK,
-                                                                  bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t, &st);
-        // every thread observes the completion of this phase, so the barrier can be re-armed safely
-        if (!st.waited) mbar_wait(st.bar, st.parity);
+        b = b_next;
+        const int gx = cur.x * BRICK + lx, gy = cur.y * BRICK + ly;
+        const int gz0 = (K == 1 ? cur.z : (cur.z & 0xFFFFFF)) * BRICK;
+        const unsigned mask = K == 1 ? 1u : (unsigned)cur.z >> 24; // CTA-uniform
+        double wx = 0.0, wy = 0.0;
+        if (inb) {
+            wx = __ldg(v.lat_x + gx);
+            wy = __ldg(v.lat_y + gy);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int gz = gz0 + 4 * h;
+            const int nvalid = v.dim_z - gz;
+            unsigned nupd = 0;
+            if (inb && nvalid > 0) {
+                const double2 wz01 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz));
+                const double2 wz23 = __ldg(reinterpret_cast<const double2 *>(v.lat_z + gz) + 1);
+                const double wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
+                unsigned flags = 0;
+#if DENSE_UNROLL_FRAMES
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+                for (int k = 0; k < K; ++k) {
+                    if (K > 1 && !((mask >> k) & 1u)) continue;
+                    double cXs, cYs, cZ;
+                    column_sums(fb.f[k], wx, wy, cXs, cYs, cZ);
+                    if (nvalid >= 4)
+                        nupd += integrate_quad_slot<UNIT_W, true, K == 1>(fb.f[k], wx, wy, cXs, cYs, cZ, wz, 4, slot,
+                                                                           rec + 4 * h, flags);
+                    else
+                        nupd += integrate_quad_slot<UNIT_W, false, K == 1>(fb.f[k], wx, wy, cXs, cYs, cZ, wz, nvalid, slot,
+                                                                            rec + 4 * h, flags);
+                }
+                if (K > 1) flush_quad(slot, rec + 4 * h, flags);
+            }
+            // Refill the slot with the quad that comes next (the brick's second quad, or the first one of
+            // this CTA's next brick): it lands while that quad's geometry and pixel loads run.  The slot's
+            // last reads (LDS) fed the arithmetic / stores above, so they have completed; a copy that was
+            // never waited for (the quad left early) must land before the next one is issued.
+            prefetch_wait<0>();
+            if (h == 0) {
+                if (inb) prefetch_quad(slot, rec + 4);
+            } else if (inb_next) {
+                prefetch_quad(slot, rec_next);
+            }
+            prefetch_commit();
+            if (nupd) atomicAdd(&s_updates[t], nupd); // no return value used: nothing waits for it
+        }
     }
+    prefetch_wait<0>();
+    unsigned my_updates = s_updates[t];
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0) { // one private slot per warp: no atomics
         const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
@@ -181,33 +306,33 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
     }
 }
 
-#else
 template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
-k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
-                  float *__restrict__ bricks, UpdateCounters uc)
+k_integrate_dense_v1(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
+                     float *__restrict__ bricks, UpdateCounters uc, int n_sm)
 {
+    // per-thread update counter in shared memory: a fire-and-forget add per column instead of a register
+    // that the 64-register budget would spill (its reload sat on the long scoreboard)
+    __shared__ unsigned s_updates[INTEGRATE_THREADS];
     const int n = *count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
-    unsigned my_updates = 0;
-    int b = blockIdx.x;
+    s_updates[t] = 0; // only this thread touches its counter: no barrier needed
+    int round = 0;
+    int b = entry_of(0, n_sm);
     int4 br_next = make_int4(0, 0, 0, 0);
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
-    for (; b < n; b += gridDim.x) {
+    while (b < n) {
         const int4 br = br_next;
-        if (b + (int)gridDim.x < n) {
-            br_next = __ldg(reinterpret_cast<const int4 *>(list) + b + gridDim.x);
-#if INTEGRATE_L2_PREFETCH
-            // one bulk-prefetch instruction pulls the next brick's 6 KB record into L2
-            if (t == 0) prefetch_record_l2(bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS);
-#endif
-        }
+        b = entry_of(++round, n_sm);
+        if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
-        my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
-                                                       bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
+        const unsigned nupd = integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
+                                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
+        if (nupd) atomicAdd(&s_updates[t], nupd);
     }
+    unsigned my_updates = s_updates[t];
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0) { // one private slot per warp: no atomics
         const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
@@ -215,7 +340,6 @@ k_integrate_dense(FrameParams f, VolumeParams v, const BrickRef *__restrict__ li
         uc.total[w] += my_updates;
     }
 }
-#endif
 
 // Stats read-out: sums the per-warp update counters and gathers the scalar counters into one block.
 __global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot,
@@ -294,6 +418,22 @@ void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int
                                                               class_cap, fs);
 }
 
+void launch_cull_bricks_batch(const FrameParams *f, const CullParams *c, FrameScratch *const *fs, int k, int nlbx, int nby,
+                              int nbz, int rank, int world, int classes, BrickRef *lists, size_t class_cap, cudaStream_t s)
+{
+    const long long n = (long long)nlbx * nby * nbz;
+    if (!n) return;
+    CullBatch cb;
+    for (int i = 0; i < DENSE_MAX_BATCH; ++i) {
+        cb.f[i] = f[i < k ? i : k - 1];
+        cb.c[i] = c[i < k ? i : k - 1];
+        cb.fs[i] = fs[i < k ? i : k - 1];
+    }
+    cb.n = k;
+    k_cull_bricks_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(cb, nlbx, nby, nbz, rank, world, classes, lists, class_cap,
+                                                                    fs[0]);
+}
+
 #ifndef INTEGRATE_RESERVE_CTAS
 #define INTEGRATE_RESERVE_CTAS 2
 #endif
@@ -308,17 +448,73 @@ void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs
 int integrate_dense_ctas_per_sm()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense<true>, INTEGRATE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense<true, 1>, INTEGRATE_THREADS, 0);
     return n > 0 ? n : 1;
+}
+
+// Single-frame launches use k_integrate_dense_v1 (measured faster at K = 1, profiles/r2_dense_ab.md);
+// TSDF_DENSE_V2=1 routes them through the staged kernel instead (A/B measurements).
+static bool dense_v1()
+{
+    static const bool v2 = getenv("TSDF_DENSE_V2") && atoi(getenv("TSDF_DENSE_V2")) != 0;
+    return !v2;
+}
+
+// SM count for entry_of(): the mapping needs the grid to be a multiple of it (1 = plain order);
+// TSDF_DENSE_ORDER=plain switches the SM-contiguous order off (A/B measurements).
+static int sm_count_for(int grid)
+{
+    static int n_sm = 0;
+    static bool plain = false;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        const char *e = getenv("TSDF_DENSE_ORDER");
+        plain = e && !strcmp(e, "plain");
+    }
+    return (!plain && n_sm > 0 && grid % n_sm == 0) ? n_sm : 1;
+}
+
+template <int K>
+static void launch_batch(const FrameParams *f, const VolumeParams &v, const BrickRef *list, const int *count, float *bricks,
+                         UpdateCounters uc, int grid, cudaStream_t s, bool unit_w)
+{
+    FrameBatch<K> fb;
+    for (int k = 0; k < K; ++k) fb.f[k] = f[k];
+    const int sms = sm_count_for(grid);
+    if (unit_w)
+        k_integrate_dense<true, K><<<grid, INTEGRATE_THREADS, 0, s>>>(fb, v, list, count, bricks, uc, sms);
+    else
+        k_integrate_dense<false, K><<<grid, INTEGRATE_THREADS, 0, s>>>(fb, v, list, count, bricks, uc, sms);
 }
 
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
                             float *bricks, UpdateCounters uc, int grid, cudaStream_t s)
 {
-    if (f.unit_w)
-        k_integrate_dense<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc);
-    else
-        k_integrate_dense<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc);
+    if (dense_v1()) {
+        const int sms = sm_count_for(grid);
+        if (f.unit_w)
+            k_integrate_dense_v1<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
+        else
+            k_integrate_dense_v1<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
+        return;
+    }
+    launch_batch<1>(&f, v, list, count, bricks, uc, grid, s, f.unit_w != 0);
+}
+
+// k frames (1..DENSE_MAX_BATCH) applied in one visit per brick; list entries carry the frame mask.
+// Batches of 3 run the K = 4 kernel with the fourth frame masked out of every entry.
+void launch_integrate_dense_batch(const FrameParams *f, int k, const VolumeParams &v, const BrickRef *list,
+                                  const int *count, float *bricks, UpdateCounters uc, int grid, cudaStream_t s)
+{
+    bool unit_w = true;
+    for (int i = 0; i < k; ++i) unit_w = unit_w && f[i].unit_w != 0;
+    FrameParams pad[DENSE_MAX_BATCH];
+    for (int i = 0; i < DENSE_MAX_BATCH; ++i) pad[i] = f[i < k ? i : k - 1];
+    if (k == 1) launch_batch<1>(pad, v, list, count, bricks, uc, grid, s, unit_w);
+    else if (k == 2) launch_batch<2>(pad, v, list, count, bricks, uc, grid, s, unit_w);
+    else launch_batch<4>(pad, v, list, count, bricks, uc, grid, s, unit_w);
 }
 
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,

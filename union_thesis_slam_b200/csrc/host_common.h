@@ -99,9 +99,13 @@ struct FrameIO {
     uint16_t *d_depth16[FRAME_SLOTS] = {}; // raw sensor depth (frame ingest path)
     // per-frame scratch, one set per frame slot: [FrameScratch | tile pyramid levels 1..3]
     // (cleared every frame), then pyramid level 0
-    FramePixel *px_slot[FRAME_SLOTS] = {}; // prepared frames (depth + folded colour, 16 B per pixel)
-    uint8_t *scratch_slot[FRAME_SLOTS] = {};
-    TilePyramid pyr_slot[FRAME_SLOTS] = {};
+    // The dense grid applies up to DENSE_MAX_BATCH frames per brick visit: every frame slot then holds
+    // `subs` prepared frames.  Flat index = sub * FRAME_SLOTS + slot, so [slot] alone is sub 0 (hash map).
+    static const int MAX_PREP = FRAME_SLOTS * DENSE_MAX_BATCH;
+    int subs = 1;
+    FramePixel *px_slot[MAX_PREP] = {}; // prepared frames (depth + folded colour, 16 B per pixel)
+    uint8_t *scratch_slot[MAX_PREP] = {};
+    TilePyramid pyr_slot[MAX_PREP] = {};
     size_t clear_bytes = 0;
     int slot = FRAME_SLOTS - 1; // scratch slot of the frame being issued (advanced by begin_kernels)
     // views of the current slot (after a frame: of the last frame issued)
@@ -132,6 +136,10 @@ struct FrameIO {
                    const uint8_t **d_rgb_out, const double **d_depth_out);
     int finish_upload(); // waits until the copy engine has left the caller's buffers (end of an integrate call)
     int ensure_px(int npix);
+    int set_subs(int n);              // prepared frames per slot (drains the streams when it grows)
+    static int prep_index(int slot, int sub) { return sub * FRAME_SLOTS + slot; }
+    int clear_sub(int sub);           // clears the scratch of prepared frame `sub` of the current slot (on `pre`)
+    int release_upload_after_prep();  // the uploaded frame is consumed by the preparation kernel alone
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
     // picks the frame's scratch slot, waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it,
     // clears FrameScratch + pyramid levels 1..3

@@ -21,6 +21,7 @@ struct FrameScratch {
     int pad;
 };
 #define DENSE_MAX_CLASSES 4
+#define DENSE_MAX_BATCH 4 // frames applied to a brick in one visit (temporal blocking)
 
 // Max valid depth per pixel tile, 4 levels: 8, 16, 32, 64 px tiles (0 = no valid pixel in the tile).
 // Level 0 is written by prep_frame, levels 1..3 by atomicMax from the same kernel (they are
@@ -65,6 +66,10 @@ int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
                             float *bricks, UpdateCounters uc, int grid, cudaStream_t s);
+void launch_cull_bricks_batch(const FrameParams *f, const CullParams *c, FrameScratch *const *fs, int k, int nlbx, int nby,
+                              int nbz, int rank, int world, int classes, BrickRef *lists, size_t class_cap, cudaStream_t s);
+void launch_integrate_dense_batch(const FrameParams *f, int k, const VolumeParams &v, const BrickRef *list,
+                                  const int *count, float *bricks, UpdateCounters uc, int grid, cudaStream_t s);
 void launch_unbrick(const float *bricks, int n_x, int dim_y, int dim_z, int nby, int nbz, float *tsdf, float *wgt,
                     float *col, int sm_count, cudaStream_t s);
 

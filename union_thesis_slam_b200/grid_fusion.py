@@ -169,6 +169,13 @@ class TSDFVolume:
     def sync(self):
         _capi.check(self._lib.tsdf_grid_sync(self._handle))
 
+    def set_batch(self, frames):
+        """Temporal blocking (tsdf_grid_set_batch): up to ``frames`` (1..4) consecutive integrate
+        calls are applied to every brick in one visit -- read once, updated by each frame in call
+        order, written once.  Results are bit-identical to frame-by-frame integration; every
+        read-out (get_volume, stats, sync, flush) first applies whatever is pending."""
+        _capi.check(self._lib.tsdf_grid_set_batch(self._handle, int(frames)))
+
     def flush(self):
         """Device-side join: the stream of cuda_stream() waits for every kernel issued so far
         (the host does not block).  Record timing events after this."""
