@@ -54,7 +54,82 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the measurement: an NVML polling
+    thread at ~1 ms (the timed region of a 20-step run lasts a few milliseconds, far below what an
+    `nvidia-smi -lms` subprocess resolves), with nvidia-smi kept as the fallback.  mark()/unmark()
+    bracket the timed region on the host clock; samples inside it are reported first, samples of the
+    whole measured section (timed region + roofline pass + end-to-end pass) beside them."""
+
+    def __init__(self, device):
+        import threading
+        self.samples = []   # (t, sm_mhz, reasons bitmask)
+        self.t0 = self.t1 = None
+        self.stop_flag = False
+        self.max_mhz = None
+        self.thread = None
+        self.fallback = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(device))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.fallback = _SmiSampler(device)
+
+    @staticmethod
+    def _physical_index(device):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if device < len(ids) and ids[device].strip().isdigit():
+                return int(ids[device])
+        return device
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def mark(self):
+        self.t0 = time.perf_counter()
+
+    def unmark(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.fallback is not None:
+            return self.fallback.stop()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+
+        def summarise(rows):
+            reasons = sorted({n for _, _, bits in rows for n, m in names if bits & m})
+            return (float(np.median([r[1] for r in rows])) if rows else None), reasons
+
+        timed = [r for r in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        sm_t, reasons_t = summarise(timed)
+        sm_all, reasons_all = summarise(self.samples)
+        return {"sm_mhz": sm_t if timed else sm_all, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(set(reasons_t) | set(reasons_all)), "samples": len(timed),
+                "samples_measured_section": len(self.samples), "sm_mhz_measured_section": sm_all,
+                "source": "NVML polling thread (1 ms); `samples` lie inside the timed region"}
+
+
+class _SmiSampler:
+    """nvidia-smi fallback of ClockSampler."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -70,7 +145,7 @@ class ClockSampler:
             pass
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi -lms 20"}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -240,64 +315,122 @@ def workload_config(world):
 
 
 # ----------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from union_thesis_slam_b200 import grid_fusion
+class Dist:
+    """World / rank plumbing shared by the dense and the hash sections."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
 
-    def allreduce(x, op):
-        if world == 1:
+    def _reduce(self, x, op):
+        if not self.dist:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def close(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_device(D, vol, step, n, first):
+    """Device time of n frames: CUDA events on the handle's own stream bracketed by barrier + synchronize,
+    max over ranks.  Returns (ms, updates summed over ranks)."""
+    torch = D.torch
+    stream = torch.cuda.ExternalStream(vol.cuda_stream(), device=D.dev)
+    u0 = vol.stats()["updated_total"]
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(n):
+        step(first + i)
+    vol.flush()  # integrate kernels run on sibling streams: join them (on the device) before the end event
+    e1.record(stream)
+    vol.sync()
+    D.barrier()
+    ms = D.max(e0.elapsed_time(e1))
+    upd = D.sum(float(vol.stats()["updated_total"] - u0))
+    return ms, upd
+
+
+def e2e_loop(D, vol, call, n, first):
+    """End to end through the public API with HOST frames: every step uploads its frame (inside the
+    integrate call) and reads a step result back.  The read-back is pipelined: step k posts its
+    counters (stats_post: a 64-byte device->host copy into pinned memory behind the step's kernels) and
+    the host consumes step k-1's, so the upload of frame k+1 overlaps the integration of frame k; every
+    step's result has been read when the clock stops.  Returns (seconds max over ranks, updates)."""
+    vol.sync()
+    D.barrier()
+    t0 = time.perf_counter()
+    upd = 0
+    prev = None
+    for i in range(n):
+        call(first + i)
+        t = vol.stats_post()
+        if prev is not None:
+            upd += vol.stats_wait(prev)["updated_last"]
+        prev = t
+    upd += vol.stats_wait(prev)["updated_last"]
+    vol.sync()
+    D.barrier()
+    return D.max(time.perf_counter() - t0), D.sum(float(upd))
+
+
+def run_b200(args):
+    from union_thesis_slam_b200 import grid_fusion
+    D = Dist()
+    torch, world, rank, local, dev = D.torch, D.world, D.rank, D.local, D.dev
 
     room, frames, K = make_frames(N_FRAMES)
     npix = IM_W * IM_H
     d_frames = [(torch.from_numpy(c).to(dev), torch.from_numpy(d).to(dev), np.linalg.inv(p)) for c, d, p in frames]
     vol = grid_fusion.TSDFVolume(room.copy(), VOXEL, rank=rank, world_size=world, device=local)
-    stream = torch.cuda.ExternalStream(vol.cuda_stream(), device=dev)
+    vol.set_batch(args.batch)
 
     def step(i):
         dc, dd, tinv = d_frames[i % N_FRAMES]
         vol.integrate_device(dc, dd, IM_H, IM_W, K, tinv, 1.0)
 
-    launches_per_step = 4  # prep_frame, cull_bricks, 2 x integrate_dense (+ one small memset)
     for i in range(args.warmup):
         step(i)
     vol.sync()
 
     # ---- timed region: frames resident in HBM, device-timed on the launching stream ----------
     sampler = ClockSampler(local) if rank == 0 else None
-    u0 = vol.stats()["updated_total"]
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    vol.flush()  # the frame's second integrate kernel runs on a sibling stream: join it before the end event
-    e1.record(stream)
-    vol.sync()
-    barrier()
-    ms = allreduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
-    clocks = sampler.stop() if sampler else None
-    upd = allreduce(float(vol.stats()["updated_total"] - u0), dist.ReduceOp.SUM if world > 1 else None)
+    if sampler:
+        sampler.mark()
+    ms, upd = timed_device(D, vol, step, args.steps, args.warmup)
+    if sampler:
+        sampler.unmark()
     value = upd / (ms * 1e-3)
+    # per frame: prep_frame, cull_bricks, 2 x integrate_dense (+ one small memset); with temporal blocking
+    # cull and integrate are launched once per batch
+    launches_per_step = 1 + 3.0 / args.batch
 
     # ---- roofline of the dominant kernel (k_integrate_dense) -----------------------------------
     # Each frame launches it twice (two independent halves of the visible bricks on sibling streams,
@@ -309,6 +442,7 @@ def run_b200(args):
     peak, peak_src = peaks()
     step_bytes = 24.0 * upd + 12.0 * npix * args.steps * world      # every rank reads the whole frame
     achieved = step_bytes / world / (ms * 1e-3) / 1e9                # per GPU
+    vol.set_batch(1)
     vol.set_profiling(True)
     k_ms, k_bytes = 0.0, 0.0
     for i in range(args.steps):
@@ -319,12 +453,13 @@ def run_b200(args):
         k_bytes += 24.0 * u + 12.0 * npix
     vol.set_profiling(False)
     serial = k_bytes / (k_ms * 1e-3) / 1e9
+    launches = 2.0 / args.batch
     roofline = {"bound": "hbm", "kernel": "k_integrate_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
                 "definition": "algorithmic bytes of the timed frames / duration of the timed region, per GPU "
                               "(the kernel's launches run back to back; overlapped prepare/cull time included)",
-                "launches_per_frame": 2,
-                "algorithmic_bytes_per_launch": step_bytes / world / args.steps / 2,
+                "launches_per_frame": launches,
+                "algorithmic_bytes_per_launch": step_bytes / world / args.steps / launches,
                 "bytes_model": "24 B x voxels updated + 12 B x pixels (SURVEY 8d)",
                 "serialised": {"achieved": serial, "frac": serial / peak,
                                "kernel_ms_per_frame": k_ms / args.steps,
@@ -338,67 +473,168 @@ def run_b200(args):
         # ncu dram__bytes_read+write of one captured launch, scaled to this run's mean launch by the
         # measured traffic/algorithmic ratio (launches differ only in how many bricks they touch)
         roofline["traffic"] = tj["ratio_traffic_over_algorithmic"] * roofline["algorithmic_bytes_per_launch"]
-        roofline["traffic_source"] = "profiles/dense_traffic.json: %.2f x algorithmic bytes (ncu, %s)" % (
+        roofline["traffic_source"] = "profiles/dense_traffic.json: %.2f x algorithmic bytes (ncu --set full, %s)" % (
             tj["ratio_traffic_over_algorithmic"], tj["kernel"])
 
-    # ---- end to end through the drop-in API: pinned host frames in, counters out, every step --
+    # ---- end to end through the drop-in API: pinned host frames in, a result out, every step ----
     h_frames = []
     for c, d, p in frames:
         pc, pd = torch.from_numpy(c).pin_memory(), torch.from_numpy(d).pin_memory()
-        h_frames.append((pc.numpy(), pd.numpy(), p, pc, pd))
-    for i in range(min(3, args.warmup)):
+        raw = torch.from_numpy(np.round(d * 1000.0).astype(np.uint16)).pin_memory()  # the sensor's own millimetres
+        h_frames.append((pc.numpy(), pd.numpy(), p, raw.numpy(), pc, pd, raw))
+
+    def call_f64(i):
         c, d, p = h_frames[i % N_FRAMES][:3]
         vol.integrate(c, d, K, p, obs_weight=1.)
+
+    def call_u16(i):
+        c, _, p, raw = h_frames[i % N_FRAMES][:4]
+        vol.integrate_raw(c, raw, K, p, obs_weight=1., depth_scale=1000., invalid_raw=65535)
+
+    for i in range(3):
+        call_f64(i)
+        call_u16(i)
+    e2e_s, e2e_upd = e2e_loop(D, vol, call_f64, args.steps, args.warmup)
+    raw_s, raw_upd = e2e_loop(D, vol, call_u16, args.steps, args.warmup)
+    # the same loop with the blocking read (stats() = device idle before the host continues), for reference
     vol.sync()
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
-    e2e_upd = 0
+    blk_upd = 0
     for i in range(args.steps):
-        c, d, p = h_frames[(args.warmup + i) % N_FRAMES][:3]
-        vol.integrate(c, d, K, p, obs_weight=1.)
-        e2e_upd += vol.stats()["updated_last"]  # device -> host read of the step's result
+        call_f64(args.warmup + i)
+        blk_upd += vol.stats()["updated_last"]
     vol.sync()
-    barrier()
-    e2e_s = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
-    e2e_upd = allreduce(float(e2e_upd), dist.ReduceOp.SUM if world > 1 else None)
+    D.barrier()
+    blk_s = D.max(time.perf_counter() - t0)
+    blk_upd = D.sum(float(blk_upd))
     e2e = {"value": e2e_upd / e2e_s, "unit": "voxel-updates/s", "h2d_bytes_per_step": npix * (8 + 3),
            "d2h_bytes_per_step": 64, "frames_per_s": args.steps / e2e_s,
-           "api": "TSDFVolume.integrate(color, depth, K, pose) + stats() per frame, pinned host buffers"}
+           "api": "TSDFVolume.integrate(color, depth f64, K, pose) every step from pinned host buffers (3.38 MB H2D "
+                  "inside the call) + stats_post(); the 64-byte counter block of step k-1 is read (stats_wait) "
+                  "while step k runs, all of them before the clock stops",
+           "raw_u16": {"value": raw_upd / raw_s, "frames_per_s": args.steps / raw_s,
+                       "h2d_bytes_per_step": npix * (2 + 3),
+                       "api": "TSDFVolume.integrate_raw: the sensor's uint16 depth, divided and masked on the device"},
+           "blocking_read": {"value": blk_upd / blk_s, "frames_per_s": args.steps / blk_s,
+                             "api": "integrate() + stats() per step: the host waits for the device every step"}}
+    clocks = sampler.stop() if sampler else None
 
     line = {
         "metric": "tsdf_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world), "frames_per_s": args.steps / (ms * 1e-3),
+        "config": dict(workload_config(world), frames_per_brick_visit=args.batch),
+        "frames_per_s": args.steps / (ms * 1e-3),
         "voxel_updates_per_step": upd / args.steps, "roofline": roofline, "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
     }
+    vol.close()
+    del d_frames, vol
+    torch.cuda.empty_cache()
 
-    if rank == 0 and world == 1 and not args.no_hash:
+    if not args.no_configs:
         try:
-            vol.close()
-            del d_frames
-            torch.cuda.empty_cache()
-            line["hash"] = bench_hash(args, dev, local, peak)
-        except Exception as exc:  # the hash line must never hide the dense result
+            line["configs"] = bench_configs(args, D)
+        except Exception as exc:  # the extra configurations must never hide the headline
+            line["configs"] = {"error": repr(exc)}
+    if not args.no_hash:
+        try:
+            line["hash"] = bench_hash(args, D)
+        except Exception as exc:
             line["hash"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_port(frames, K, room, VOXEL, steps=4, warmup=1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "host_cpus")}
+        line["cpu_baseline"] = cpu_baselines(frames, K, room)
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 
-def bench_hash(args, dev, local, peak, rank=0, world=1):
+def cpu_baselines(frames, K, room):
+    """The reference's own numba CPU path (oracle/_ref, kind "reference") on a bounded sample of the headline
+    workload, with its C/OpenMP restatement ("port") timed beside it; only the port when oracle/_ref is absent."""
+    keep = ("value", "unit", "cores", "kind", "sample", "cpu_model", "host_cpus", "voxel_visits_per_s",
+            "threading_layer", "numba", "numpy", "frames_per_s_sample")
+    port = cpu_port(frames, K, room, VOXEL, steps=4, warmup=1)
+    out = {k: port[k] for k in keep if k in port}
+    if reference_built():
+        try:
+            ref = cpu_reference(frames, K, room, VOXEL, steps=3, warmup=1, slabs=4)
+            out = {k: ref[k] for k in keep if k in ref}
+            out["port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:
+            out["reference_error"] = repr(exc)
+    return out
+
+
+def fixture_frames():
+    """The 12 frames of the bundled sequence kept under tests/golden/frames, decoded as grid_demo1.py:80-84."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import frames as fx
+    import scenes
+    idx = list(range(10)) + [500, 999]
+    return [fx.load_frame(i, check=False) for i in idx], fx.intrinsics(), np.array(scenes.CONFIG1_BOUNDS)
+
+
+def bench_configs(args, D):
+    """The other dense configurations of BASELINE.json, device-timed with frames resident, each with its
+    roofline figure: configs[0] (bundled frames, 2 cm; launch-bound, so also with 4 frames per brick
+    visit), configs[2] (bundled frames, 5 mm) and the 48 GB reading of configs[3] (4.64 mm room)."""
+    from union_thesis_slam_b200 import grid_fusion, synth
+    torch, dev = D.torch, D.dev
+    peak, _ = peaks()
+    out = {}
+
+    def run(name, bounds, voxel, frs, Kc, batch, passes, note):
+        H, W = frs[0][1].shape
+        dfr = [(torch.from_numpy(np.ascontiguousarray(c)).to(dev), torch.from_numpy(d).to(dev), np.linalg.inv(p))
+               for c, d, p in frs]
+        vol = grid_fusion.TSDFVolume(bounds.copy(), voxel, rank=D.rank, world_size=D.world, device=D.local)
+        vol.set_batch(batch)
+
+        def step(i):
+            dc, dd, ti = dfr[i % len(dfr)]
+            vol.integrate_device(dc, dd, H, W, Kc, ti, 1.0)
+
+        for i in range(len(dfr)):       # first pass: every voxel of the trajectory seen once
+            step(i)
+        n = passes * len(dfr)
+        ms, upd = timed_device(D, vol, step, n, 0)
+        dim = [int(x) for x in vol._vol_dim]
+        vol.close()
+        del vol, dfr
+        torch.cuda.empty_cache()
+        gbs = (24.0 * upd + 12.0 * H * W * n * D.world) / D.world / (ms * 1e-3) / 1e9
+        out[name] = {"workload": note, "grid": dim, "voxel_size_m": voxel, "frames_per_brick_visit": batch,
+                     "steps": n, "ms_per_step": ms / n, "frames_per_s": n / (ms * 1e-3), "value": upd / (ms * 1e-3),
+                     "unit": "voxel-updates/s", "voxel_updates_per_step": upd / n, "n_gpus": D.world,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}}
+
+    if D.world == 1:
+        frs, Kf, bounds = fixture_frames()
+        for batch in (1, 4):
+            run("config0_2cm_batch%d" % batch, bounds, 0.02, frs, Kf, batch, 8,
+                "BASELINE.json configs[0]: 12 frames of the bundled 640x480 sequence (tests/golden/frames) cycled, "
+                "dense grid at 2 cm over the sequence's bounds")
+        run("config2_5mm", bounds, 0.005, frs, Kf, 1, 2,
+            "BASELINE.json configs[2]: the bundled frames cycled into a 5 mm grid over the same bounds (23.6 GB)")
+    room = synth.room_bounds(ROOM)
+    frs, Kr = synth.room_stream(8, room, seed=0)
+    run("config3_48GB_reading", room, 0.00464, frs, Kr, 1, 1,
+        "BASELINE.json configs[3] read as '~4e9 voxels, ~48 GB': the same 10x10x4 m room at 4.64 mm, "
+        "first 8 frames of the headline trajectory")
+    return out
+
+
+def bench_hash(args, D):
     """Voxel-block hash map, BASELINE.json configs[4]-shaped: 1280x720 synthetic depth stream on a
     seeded trajectory through a 40 x 40 x 6 m room at 2 cm voxels (8^3 blocks; the bounded block grid
-    holds 2.4 M blocks), single GPU.  Frames resident in HBM; whole-pipeline device time."""
-    import torch
+    holds 2.4 M blocks), blocks sharded over the ranks by owner hash (every rank walks every frame, no
+    per-frame collective).  Frames resident in HBM; whole-pipeline device time; then end to end."""
     from union_thesis_slam_b200 import hash_fusion, synth
+    torch, dev, world, rank, local = D.torch, D.dev, D.world, D.rank, D.local
+    peak, _ = peaks()
     room = synth.room_bounds(HASH_ROOM)
     frames, K = synth.room_stream(N_FRAMES, room, width=HASH_W, height=HASH_H, seed=1)
     nblocks = int(np.prod(np.ceil(np.array(HASH_ROOM) / HASH_VOXEL / 8)))
@@ -413,34 +649,22 @@ def bench_hash(args, dev, local, peak, rank=0, world=1):
         dc, dd, ti = d_frames[i % N_FRAMES]
         ht.integrate_device(dc, dd, HASH_H, HASH_W, K, ti, 1.0)
 
-    import torch.distributed as dist
-
-    def allreduce(x, op):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
-        return float(t.item())
-
     for i in range(max(args.warmup, N_FRAMES)):  # one full pass allocates the blocks of the trajectory
         step(i)
     ht.sync()
     s0 = ht.stats()
     stream = torch.cuda.ExternalStream(ht.cuda_stream(), device=dev)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(steps):
         step(i)
     e1.record(stream)  # the frame's integrate kernel is the last kernel of its pipeline
     ht.sync()
-    if world > 1:
-        dist.barrier()
-    wall = allreduce(e0.elapsed_time(e1) * 1e-3, dist.ReduceOp.MAX if world > 1 else None)
+    D.barrier()
+    wall = D.max(e0.elapsed_time(e1) * 1e-3)
     s1 = ht.stats()
-    upd = allreduce(float(s1["updated_total"] - s0["updated_total"]), dist.ReduceOp.SUM if world > 1 else None)
+    upd = D.sum(float(s1["updated_total"] - s0["updated_total"]))
     # algorithmic bytes of the same frames (second pass, per-frame counters)
     tot_bytes = 0.0
     for i in range(steps):
@@ -448,21 +672,93 @@ def bench_hash(args, dev, local, peak, rank=0, world=1):
         st = ht.stats()
         tot_bytes += 24.0 * st["updated_last"] + 16.0 * (st["blocks_visited_last"] + st["keys_inserted_last"]) \
             + 12.0 * HASH_W * HASH_H
-    tot_bytes = allreduce(tot_bytes, dist.ReduceOp.SUM if world > 1 else None)
-    blocks_all = allreduce(float(s1["blocks"]), dist.ReduceOp.SUM if world > 1 else None)
+    tot_bytes = D.sum(tot_bytes)
+    blocks_all = D.sum(float(s1["blocks"]))
     achieved = tot_bytes / wall / 1e9 / world  # per GPU, against one GPU's HBM peak
-    return {"metric": "tsdf_voxel_updates_per_s", "value": upd / wall, "unit": "voxel-updates/s", "n_gpus": world,
-            "blocks_allocated_all_ranks": int(blocks_all),
-            "frames_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps,
-            "workload": "BASELINE.json configs[4]: 1280x720 stream, 40x40x6 m room, 2 cm voxels, 8^3 blocks",
-            "voxel_size_m": HASH_VOXEL, "blocks_allocated": s1["blocks"], "table_keys": s1["table_keys"],
-            "table_slots": s1["table_slots"], "heap_capacity": s1["heap_capacity"],
-            "voxel_updates_per_step": upd / steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "bytes_model": "24 B x voxels updated + 16 B x unique keys (visible + inserted) + 12 B x "
-                                        "pixels, over the device time (CUDA events, max over ranks) of the whole "
-                                        "pipeline: prepare, allocation (super-block scan, refine + lock-free insert), "
-                                        "compaction, integrate"}}
+
+    # end to end: HashTable.integrate with pinned host frames, a pipelined per-step read-back (see e2e_loop)
+    h_frames = []
+    for c, d, p in frames:
+        pc, pd = torch.from_numpy(c).pin_memory(), torch.from_numpy(d).pin_memory()
+        h_frames.append((pc.numpy(), pd.numpy(), p, pc, pd))
+
+    def call(i):
+        c, d, p = h_frames[i % N_FRAMES][:3]
+        ht.integrate(c, d, K, p, obs_weight=1.)
+
+    for i in range(2):
+        call(i)
+    e2e_s, e2e_upd = e2e_loop(D, ht, call, steps, 2)
+    out = {"metric": "tsdf_voxel_updates_per_s", "value": upd / wall, "unit": "voxel-updates/s", "n_gpus": world,
+           "blocks_allocated_all_ranks": int(blocks_all),
+           "frames_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps,
+           "workload": "BASELINE.json configs[4]: 1280x720 stream, 40x40x6 m room, 2 cm voxels, 8^3 blocks",
+           "voxel_size_m": HASH_VOXEL, "blocks_allocated": s1["blocks"], "table_keys": s1["table_keys"],
+           "table_slots": s1["table_slots"], "heap_capacity": s1["heap_capacity"],
+           "voxel_updates_per_step": upd / steps, "scaling": "strong",
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "bytes_model": "24 B x voxels updated + 16 B x unique keys (visible + inserted) + 12 B x "
+                                       "pixels, over the device time (CUDA events, max over ranks) of the whole "
+                                       "pipeline: prepare, allocation (super-block scan, refine + lock-free insert), "
+                                       "compaction, integrate",
+                        "traffic": None},
+           "e2e": {"value": e2e_upd / e2e_s, "unit": "voxel-updates/s", "frames_per_s": steps / e2e_s,
+                   "h2d_bytes_per_step": HASH_W * HASH_H * (8 + 3), "d2h_bytes_per_step": 96,
+                   "api": "HashTable.integrate(color, depth f64, K, pose) from pinned host buffers + stats_post(); "
+                          "step k-1's counters are read while step k runs"}}
+    tf = os.path.join(ROOT, "profiles", "hash_traffic.json")
+    if os.path.exists(tf):
+        with open(tf) as fh:
+            tj = json.load(fh)
+        out["roofline"]["traffic"] = tj["ratio_traffic_over_algorithmic"] * tot_bytes / world / steps
+        out["roofline"]["traffic_source"] = "profiles/hash_traffic.json: %.2f x algorithmic bytes per frame (ncu, %s)" % (
+            tj["ratio_traffic_over_algorithmic"], tj["kernel"])
+    ht.close()
+    del d_frames
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_hash_port(frames[:3], K)
+    return out
+
+
+def cpu_hash_port(frames, K, room_size=(8.0, 8.0, 3.0)):
+    """CPU side of the hash line: the reference HashTable restated per voxel (oracle.OracleHashVox, C/OpenMP) on a
+    room the host can hold -- the reference's own HashTable.integrate is a pure-Python loop at ~2e4 voxel-updates/s
+    (BASELINE.md), timed here on one frame of a small room when oracle/_ref is present."""
+    from oracle import oracle
+    from union_thesis_slam_b200 import synth
+    room = synth.room_bounds(room_size)
+    fr, Kc = synth.room_stream(3, room, width=HASH_W, height=HASH_H, seed=5)
+    orh = oracle.OracleHashVox(room.copy(), HASH_VOXEL)
+    orh.integrate(fr[0][0], fr[0][1], Kc, fr[0][2])
+    t0 = time.perf_counter()
+    upd = 0
+    for c, d, p in fr[1:]:
+        upd += orh.integrate(c, d, Kc, p)
+    dt = time.perf_counter() - t0
+    out = {"value": upd / dt, "unit": "voxel-updates/s", "cores": int(oracle.lib().oracle_max_threads()), "kind": "port",
+           "sample": "%gx%gx%g m room at 2 cm, 1280x720, 2 frames, per-voxel float64 entries (oracle.OracleHashVox)" % room_size}
+    if reference_built():
+        try:
+            import contextlib
+            import io
+            from oracle import build_ref
+            _, hf = build_ref.load()
+            small = synth.room_bounds((2.0, 2.0, 2.0))
+            frs, Ks = synth.room_stream(2, small, width=HASH_W, height=HASH_H, seed=5)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = hf.HashTable(small.copy(), HASH_VOXEL, map_size=2000000)
+                t0 = time.perf_counter()
+                ref.integrate(frs[0][0], frs[0][1], Ks, frs[0][2])
+                dt = time.perf_counter() - t0
+                n = ref.count_num_hash_entries()
+            out = {"value": n / dt, "unit": "voxel-updates/s", "cores": 1, "kind": "reference",
+                   "sample": "reference HashTable.integrate (pure-Python per-voxel loop), one 1280x720 frame into a "
+                             "2x2x2 m room at 2 cm: %d voxel entries in %.1f s" % (n, dt),
+                   "port": out}
+        except Exception as exc:
+            out["reference_error"] = repr(exc)
+    return out
 
 
 def main():
@@ -485,6 +781,9 @@ def _main(out):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-hash", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra dense configurations (configs 0, 2, 48 GB)")
+    ap.add_argument("--batch", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="frames applied per brick visit in the device-timed region (temporal blocking)")
     ap.add_argument("--port", action="store_true", help="--impl reference: time the C/OpenMP port instead of oracle/_ref")
     ap.add_argument("--workload", default="dense", choices=["dense", "hash"],
                     help="hash: print the hash-map line alone (works under torchrun: blocks sharded by owner hash)")
@@ -499,23 +798,13 @@ def _main(out):
 
 
 def run_hash_only(args):
-    """Hash map alone, optionally sharded over the ranks of a torchrun launch (owner-hashed blocks,
-    every rank walks every frame, no per-frame collective)."""
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    line = bench_hash(args, torch.device("cuda", local), local, peaks()[0], rank, world)
-    line.update({"higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f64"})
-    if rank == 0:
+    """Hash map alone, optionally sharded over the ranks of a torchrun launch."""
+    D = Dist()
+    line = bench_hash(args, D)
+    line.update({"higher_is_better": True, "data": "synthetic", "dtype": "f64"})
+    if D.rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

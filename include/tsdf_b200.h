@@ -88,6 +88,14 @@ int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs);
 /* counters[0] voxels updated by the last frame, [1] voxels updated since create,
  * [2] bricks visited by the last frame, [3] frames integrated. */
 int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4]);
+/* The same counters without stalling the pipeline: post() enqueues a snapshot behind everything issued
+ * so far (one tiny kernel + a 64-byte device->host copy into pinned memory) and returns a ticket at once;
+ * wait() blocks until THAT snapshot has landed -- not until the device is idle -- and returns it.  A
+ * caller that integrates frame k, posts, and then reads the ticket of frame k-1 gets every frame's
+ * result while the upload of frame k+1 overlaps the integration of frame k (the reference's loop,
+ * grid_demo1.py:76-87, has no per-frame read-back at all).  The last 16 tickets stay readable. */
+int tsdf_grid_stats_post(tsdf_grid *g, int64_t *ticket);
+int tsdf_grid_stats_wait(tsdf_grid *g, int64_t ticket, int64_t counters[4]);
 int tsdf_grid_sync(tsdf_grid *g);
 /* Measurement aids.  Timing events are recorded only while profiling is on:
  *   set_profiling(2): frame timing -- last_kernel_ms() = device milliseconds from the first
@@ -148,6 +156,19 @@ int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_dept
  * [10] frames integrated, [11] candidate keys emitted by the last frame's ray walk. */
 int vh_stats(tsdf_hash *h, int64_t stats[12]);
 int vh_num_blocks(tsdf_hash *h, int64_t *n);
+/* Per-voxel view of the block map -- HashTable.get_hash_entry / get_voxel (hash_fusion.py:285-320) and
+ * remove (hash_fusion.py:322-393) on the table that integrate() fills.  coords: n voxel indices
+ * [n][3]; a voxel has an entry iff its block owns storage and its weight is > 0 (the reference
+ * creates the entry when it first updates the voxel, hash_fusion.py:138-143).
+ *   mode 0: out[i] = {sdf, weight, colour (float encoding B*65536+G*256+R)}, found[i] = 0/1
+ *   mode 1: like 0, and every found voxel returns to the no-entry state (sdf 1, weight 0, colour 0).
+ * With world > 1 each rank answers for the blocks it owns.  out / found are HOST arrays, may be NULL. */
+int vh_voxel_query(tsdf_hash *h, const int32_t *coords, int64_t n, int mode, float *out, uint8_t *found);
+/* count_num_hash_entries (hash_fusion.py:147-154) in the reference's unit: voxels that have an entry. */
+int vh_count_voxels(tsdf_hash *h, int64_t *count);
+/* Non-blocking variant of vh_stats, same contract as tsdf_grid_stats_post / _wait. */
+int vh_stats_post(tsdf_hash *h, int64_t *ticket);
+int vh_stats_wait(tsdf_hash *h, int64_t ticket, int64_t stats[12]);
 
 /* Block export: keys[n][3] int32 block coordinates (voxel // 8), payload[n][1536] float32
  * (tsdf | weight | colour, voxel order x*64 + y*8 + z inside the block).  Call with NULL

@@ -285,3 +285,51 @@ def test_allocation_front_ends_agree(monkeypatch):
         ht.close()
     assert out["walk"][2] == out["grid"][2] > 0
     assert np.array_equal(out["walk"][0], out["grid"][0]) and np.array_equal(out["walk"][1], out["grid"][1])
+
+
+def test_integrate_and_per_voxel_calls_see_one_map():
+    """Reference hash_fusion.py:285-320, 147-154: a voxel inserted by HashTable.integrate is found by
+    get_hash_entry / get_voxel, and count_num_hash_entries counts voxel entries.  Frame 0 of the
+    bundled sequence at 2 cm: the reference's own count is 354 383 (its committed pstats dump)."""
+    from union_thesis_slam_b200 import hash_fusion
+    K = frames.intrinsics()
+    c, d, p = frames.load_frame(0)
+    ht = hash_fusion.HashTable(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL, map_size=1 << 16)
+    orc = oracle.OracleHashVox(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    ht.integrate(c, d, K, p)
+    orc.integrate(c, d, K, p)
+    lf0, ne0 = ht.get_load_factor(), ht.get_num_non_empty_bucket()
+    assert ht.count_num_hash_entries() == 354383 == int(orc.entries.sum())
+    rng = np.random.default_rng(9)
+    hit = np.argwhere(orc.entries)
+    miss = np.argwhere(orc.entries == 0)
+    hit = hit[rng.choice(len(hit), 1000, replace=False)]
+    miss = miss[rng.choice(len(miss), 1000, replace=False)]
+    found, sdf, wgt, col = ht.query_voxels(np.concatenate([hit, miss]))
+    assert found[:1000].all() and not found[1000:].any()
+    i = tuple(hit.T)
+    assert np.array_equal(wgt[:1000], orc.weight[i].astype(np.float32))
+    assert float(np.abs(sdf[:1000].astype(np.float64) - orc.sdf[i]).max()) <= 1e-5
+    assert np.array_equal(col[:1000], orc.color[i].astype(np.float32))
+    # object API, one voxel at a time (snapshots of the device map)
+    for v in hit[:5]:
+        e = ht.get_hash_entry(v)
+        assert e is not None and list(e.get_position()) == [int(x) for x in v]
+        vox = ht.get_voxel(v)
+        assert vox.get_weight() == orc.weight[tuple(v)] and abs(vox.get_sdf() - orc.sdf[tuple(v)]) <= 1e-5
+        assert vox.get_color() == orc.color[tuple(v)]
+    for v in miss[:5]:
+        assert ht.get_hash_entry(v) is None and ht.get_voxel(v) is None
+    assert ht.get_hash_entry([-3, 0, 0]) is None and ht.get_hash_entry([10 ** 6, 0, 0]) is None
+    # look-ups neither create the hand-fed container nor change what the metrics report
+    assert ht._voxels is None and (ht.get_load_factor(), ht.get_num_non_empty_bucket()) == (lf0, ne0)
+    # remove (hash_fusion.py:322-329) on a voxel written by integrate
+    ht.remove(hit[0])
+    assert ht.get_hash_entry(hit[0]) is None and ht.count_num_hash_entries() == 354382
+    t, w, _ = ht.get_volume_with_weight()
+    assert t[tuple(hit[0])] == 1.0 and w[tuple(hit[0])] == 0.0
+    # hand-added entries live beside the integrated ones and are counted with them
+    from union_thesis_slam_b200 import bucket_table
+    ht.add_hash_entry(bucket_table.HashEntry([1, 2, 3], None, bucket_table.Voxel()))
+    assert ht.get_hash_entry([1, 2, 3]) is not None and ht.count_num_hash_entries() == 354383
+    assert ht.get_hash_entry(hit[1]) is not None

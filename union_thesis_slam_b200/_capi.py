@@ -32,6 +32,8 @@ SYMBOLS = [
     ("tsdf_grid_download_device", _i, [_p, _p, _p, _p]),
     ("tsdf_grid_local_x", _i, [_p, _p, _p]),
     ("tsdf_grid_stats", _i, [_p, _p]),
+    ("tsdf_grid_stats_post", _i, [_p, _p]),
+    ("tsdf_grid_stats_wait", _i, [_p, _i64, _p]),
     ("tsdf_grid_sync", _i, [_p]),
     ("tsdf_grid_last_kernel_ms", _i, [_p, _p]),
     ("tsdf_grid_set_profiling", _i, [_p, _i]),
@@ -46,6 +48,10 @@ SYMBOLS = [
     ("vh_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("vh_stats", _i, [_p, _p]),
     ("vh_num_blocks", _i, [_p, _p]),
+    ("vh_voxel_query", _i, [_p, _p, _i64, _i, _p, _p]),
+    ("vh_count_voxels", _i, [_p, _p]),
+    ("vh_stats_post", _i, [_p, _p]),
+    ("vh_stats_wait", _i, [_p, _i64, _p]),
     ("vh_export_blocks", _i, [_p, _i64, _p, _p, _p]),
     ("vh_to_dense", _i, [_p, _p, _p, _p]),
     ("vh_to_dense_device", _i, [_p, _p, _p, _p]),

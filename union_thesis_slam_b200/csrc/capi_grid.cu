@@ -510,6 +510,34 @@ int CounterStore::init(int n_warps)
     CUDA_TRY(cudaMemset(total, 0, (size_t)n * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&d_stats, sizeof(StatsBlock)));
     CUDA_TRY(cudaMallocHost(&h_stats, sizeof(StatsBlock)));
+    CUDA_TRY(cudaMalloc(&d_ring, STATS_RING * sizeof(StatsBlock)));
+    CUDA_TRY(cudaMallocHost(&h_ring, STATS_RING * sizeof(StatsBlock)));
+    for (int i = 0; i < STATS_RING; ++i) CUDA_TRY(cudaEventCreateWithFlags(&ring_done[i], cudaEventDisableTiming));
+    return TSDF_OK;
+}
+
+int CounterStore::post(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries, const int *heap_top,
+                       cudaStream_t s, int64_t frames, int64_t *ticket)
+{
+    const int r = (int)(next_ticket % STATS_RING);
+    launch_collect_stats(view(slot), n, fs, tot, n_entries, heap_top, d_ring + r, s);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_ring + r, d_ring + r, sizeof(StatsBlock), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(ring_done[r], s));
+    ring_frames[r] = frames;
+    *ticket = next_ticket++;
+    return TSDF_OK;
+}
+
+int CounterStore::wait(int64_t ticket, const StatsBlock **out, int64_t *frames)
+{
+    BAD_ARG(ticket < 0 || ticket >= next_ticket, "unknown stats ticket %lld", (long long)ticket);
+    BAD_ARG(next_ticket - ticket > STATS_RING, "stats ticket %lld is too old (only the last %d snapshots are kept)",
+            (long long)ticket, STATS_RING);
+    const int r = (int)(ticket % STATS_RING);
+    CUDA_TRY(cudaEventSynchronize(ring_done[r]));
+    *out = h_ring + r;
+    *frames = ring_frames[r];
     return TSDF_OK;
 }
 
@@ -520,6 +548,10 @@ void CounterStore::release()
     if (total) cudaFree(total);
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
+    if (d_ring) cudaFree(d_ring);
+    if (h_ring) cudaFreeHost(h_ring);
+    for (int i = 0; i < STATS_RING; ++i)
+        if (ring_done[i]) cudaEventDestroy(ring_done[i]);
 }
 
 int CounterStore::collect(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries,
@@ -859,6 +891,31 @@ extern "C" int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4])
     counters[1] = (int64_t)st->updated_total;
     counters[2] = g->frames > 0 ? (int64_t)st->vis_count : 0;
     counters[3] = g->frames;
+    return TSDF_OK;
+}
+
+extern "C" int tsdf_grid_stats_post(tsdf_grid *g, int64_t *ticket)
+{
+    BAD_ARG(!g || !ticket, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    int rc = grid_flush_batch(g);
+    if (rc || (rc = g->io.join())) return rc;
+    const int slot = g->frames > 0 ? g->io.slot : 0;
+    return g->counters.post(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, g->frames, ticket);
+}
+
+extern "C" int tsdf_grid_stats_wait(tsdf_grid *g, int64_t ticket, int64_t counters[4])
+{
+    BAD_ARG(!g || !counters, "NULL argument");
+    CUDA_TRY(cudaSetDevice(g->device));
+    const StatsBlock *st = nullptr;
+    int64_t frames = 0;
+    int rc = g->counters.wait(ticket, &st, &frames);
+    if (rc) return rc;
+    counters[0] = frames > 0 ? (int64_t)st->updated_last : 0;
+    counters[1] = (int64_t)st->updated_total;
+    counters[2] = frames > 0 ? (int64_t)st->vis_count : 0;
+    counters[3] = frames;
     return TSDF_OK;
 }
 

@@ -274,25 +274,19 @@ extern "C" int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const dou
     return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
 }
 
-extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
+static int hash_fill_stats(tsdf_hash *h, const StatsBlock *st, int64_t frames, int64_t stats[12])
 {
-    BAD_ARG(!h || !stats, "NULL argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    const StatsBlock *st = nullptr;
-    const int slot = h->frames > 0 ? h->io.slot : 0;
-    int rc = h->counters.collect(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.compute, &st);
-    if (rc) return rc;
     stats[0] = h->heap_blocks - st->heap_top;
     stats[1] = st->n_entries;
     stats[2] = h->table_slots;
     stats[3] = h->heap_blocks;
     stats[4] = st->heap_top;
-    stats[5] = h->frames > 0 ? (int64_t)st->updated_last : 0;
+    stats[5] = frames > 0 ? (int64_t)st->updated_last : 0;
     stats[6] = (int64_t)st->updated_total;
     stats[7] = (int64_t)st->last_visited;
     stats[8] = (int64_t)st->max_probe;
     stats[9] = st->new_keys;
-    stats[10] = h->frames;
+    stats[10] = frames;
     stats[11] = st->cand_count;
     if (st->error) {
         const int code = -(int)st->error;
@@ -303,6 +297,36 @@ extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
         return code;
     }
     return TSDF_OK;
+}
+
+extern "C" int vh_stats(tsdf_hash *h, int64_t stats[12])
+{
+    BAD_ARG(!h || !stats, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const StatsBlock *st = nullptr;
+    const int slot = h->frames > 0 ? h->io.slot : 0;
+    int rc = h->counters.collect(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.compute, &st);
+    if (rc) return rc;
+    return hash_fill_stats(h, st, h->frames, stats);
+}
+
+extern "C" int vh_stats_post(tsdf_hash *h, int64_t *ticket)
+{
+    BAD_ARG(!h || !ticket, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int slot = h->frames > 0 ? h->io.slot : 0;
+    return h->counters.post(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.compute, h->frames, ticket);
+}
+
+extern "C" int vh_stats_wait(tsdf_hash *h, int64_t ticket, int64_t stats[12])
+{
+    BAD_ARG(!h || !stats, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const StatsBlock *st = nullptr;
+    int64_t frames = 0;
+    int rc = h->counters.wait(ticket, &st, &frames);
+    if (rc) return rc;
+    return hash_fill_stats(h, st, frames, stats);
 }
 
 extern "C" int vh_num_blocks(tsdf_hash *h, int64_t *n)
@@ -435,5 +459,64 @@ extern "C" int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, in
         }
     }
     if (removed) *removed = count;
+    return TSDF_OK;
+}
+
+// Per-voxel view of the block map: HashTable.get_hash_entry / get_voxel / remove on the table that
+// integrate() fills (reference hash_fusion.py:285-320, 322-393).  mode 0 = look up, 1 = remove.
+extern "C" int vh_voxel_query(tsdf_hash *h, const int32_t *coords, int64_t n, int mode, float *out, uint8_t *found)
+{
+    BAD_ARG(!h || (!coords && n > 0), "NULL argument");
+    BAD_ARG(n < 0 || n > ((int64_t)1 << 28), "bad query count");
+    BAD_ARG(mode != 0 && mode != 1, "mode %d (0 look up, 1 remove)", mode);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!n) return TSDF_OK;
+    cudaStream_t s = h->io.compute;
+    int32_t *d_coords = nullptr;
+    float *d_out = nullptr;
+    uint8_t *d_found = nullptr;
+    cudaError_t e = cudaMalloc(&d_coords, (size_t)n * 3 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_found, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_coords, coords, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        launch_voxel_query(h->dev, d_coords, (int)n, mode, d_out, d_found, s);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && out) e = cudaMemcpyAsync(out, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && found) e = cudaMemcpyAsync(found, d_found, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (d_coords) cudaFree(d_coords);
+    if (d_out) cudaFree(d_out);
+    if (d_found) cudaFree(d_found);
+    if (e != cudaSuccess) {
+        tsdf_set_error("voxel query failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? TSDF_ERR_OOM : TSDF_ERR_CUDA;
+    }
+    return TSDF_OK;
+}
+
+// Number of voxels that have an entry in the reference's sense (weight > 0): count_num_hash_entries.
+extern "C" int vh_count_voxels(tsdf_hash *h, int64_t *count)
+{
+    BAD_ARG(!h || !count, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->io.compute;
+    unsigned long long *d_total = nullptr, total = 0;
+    CUDA_TRY(cudaMalloc(&d_total, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s);
+    if (e == cudaSuccess) {
+        launch_count_voxels(h->dev, d_total, h->sm_count, s);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_total);
+    if (e != cudaSuccess) {
+        tsdf_set_error("voxel count failed: %s", cudaGetErrorString(e));
+        return TSDF_ERR_CUDA;
+    }
+    *count = (int64_t)total;
     return TSDF_OK;
 }

@@ -395,6 +395,70 @@ __global__ void k_remove_blocks(HashDev h, const int32_t *keys, int n, int *remo
     atomicAdd(removed, 1);
 }
 
+// Per-voxel view of the block map (reference hash_fusion.py:285-320: get_hash_entry / get_voxel on the
+// table that integrate() fills).  coords are VOXEL indices; a voxel "has an entry" iff its block owns
+// storage and its weight is > 0 (the reference creates an entry exactly when it first updates a voxel).
+//   mode 0: look up -- out[i] = (tsdf, weight, colour as the reference's float encoding), found[i] = 0/1
+//   mode 1: remove  -- a found voxel goes back to the no-entry state (tsdf 1, weight 0, colour 0;
+//                      hash_fusion.py:322-393 at voxel granularity), found[i] reports whether it existed
+__global__ void k_voxel_query(HashDev h, const int32_t *__restrict__ coords, int n, int mode, float *__restrict__ out,
+                              uint8_t *__restrict__ found)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+    bool ok = false;
+    float t = 1.0f, w = 0.0f, c = 0.0f;
+    if (x >= 0 && y >= 0 && z >= 0 && (x >> 3) < h.nbx && (y >> 3) < h.nby && (z >> 3) < h.nbz) {
+        const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+        const int slot = table_find(h, pack_key(bx, by, bz), bx, by, bz);
+        const uint32_t storage = slot >= 0 ? h.vals[slot] : VAL_NONE;
+        if (storage != VAL_NONE) {
+            float *rec = h.blocks + (size_t)storage * BRICK_FLOATS + ((x & 7) * 64 + (y & 7) * 8 + (z & 7));
+            w = rec[BRICK_VOX];
+            if (w > 0.0f) {
+                ok = true;
+                t = rec[0];
+                c = (float)__float_as_uint(rec[2 * BRICK_VOX]);
+                if (mode == 1) {
+                    rec[0] = 1.0f;
+                    rec[BRICK_VOX] = 0.0f;
+                    rec[2 * BRICK_VOX] = 0.0f;
+                }
+            }
+        }
+    }
+    if (out) { out[3 * i] = t; out[3 * i + 1] = ok ? w : 0.0f; out[3 * i + 2] = ok ? c : 0.0f; }
+    if (found) found[i] = ok ? 1 : 0;
+}
+
+// Number of voxels with weight > 0 over all blocks that own storage == the reference map's entry
+// count (hash_fusion.py:147-154), which is what the thesis' space comparison reports.
+__global__ void k_count_voxels(HashDev h, unsigned long long *total)
+{
+    const int n = *h.n_entries;
+    unsigned cnt = 0;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t storage = h.vals[h.entries[e]];
+        if (storage == VAL_NONE) continue;
+        const float *wp = h.blocks + (size_t)storage * BRICK_FLOATS + BRICK_VOX;
+        for (int i = threadIdx.x; i < BRICK_VOX; i += blockDim.x) cnt += wp[i] > 0.0f;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
+void launch_voxel_query(const HashDev &h, const int32_t *coords, int n, int mode, float *out, uint8_t *found, cudaStream_t s)
+{
+    if (n <= 0) return;
+    k_voxel_query<<<(n + 127) / 128, 128, 0, s>>>(h, coords, n, mode, out, found);
+}
+
+void launch_count_voxels(const HashDev &h, unsigned long long *total, int sm_count, cudaStream_t s)
+{
+    k_count_voxels<<<sm_count * 8, 128, 0, s>>>(h, total);
+}
+
 // ---------------------------------------------------------------------------------------------
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s) { k_hash_init<<<sm_count * 4, 256, 0, s>>>(h); }
 

@@ -66,6 +66,17 @@ struct CounterStore {
     // one kernel + one D2H copy + one stream sync; returns the pinned mirror
     int collect(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries, const int *heap_top,
                 cudaStream_t s, const StatsBlock **out);
+    // Non-blocking variant: post() enqueues the same kernel + D2H copy into ring slot (ticket % STATS_RING)
+    // and records an event; wait() blocks on that event only, so a caller that reads frame k-1's
+    // counters while frame k runs never stalls the pipeline (the upload of frame k+1 overlaps frame k).
+    static const int STATS_RING = 16;
+    StatsBlock *d_ring = nullptr, *h_ring = nullptr;
+    cudaEvent_t ring_done[STATS_RING] = {};
+    int64_t ring_frames[STATS_RING] = {};
+    int64_t next_ticket = 0;
+    int post(int slot, const FrameScratch *fs, const Totals *tot, const int *n_entries, const int *heap_top,
+             cudaStream_t s, int64_t frames, int64_t *ticket);
+    int wait(int64_t ticket, const StatsBlock **out, int64_t *frames);
 };
 int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H, int W, const double K[9],
                       const double Tinv[16], double obs);

@@ -166,6 +166,20 @@ class TSDFVolume:
         return dict(updated_last=int(c[0]), updated_total=int(c[1]), bricks_visited_last=int(c[2]),
                     frames=int(c[3]))
 
+    def stats_post(self):
+        """Non-blocking stats: enqueues a snapshot of the counters behind everything issued so far and
+        returns a ticket for stats_wait().  Reading frame k-1's ticket after integrating frame k keeps
+        the device busy (tsdf_grid_stats_post)."""
+        t = C.c_int64()
+        _capi.check(self._lib.tsdf_grid_stats_post(self._handle, C.byref(t)))
+        return t.value
+
+    def stats_wait(self, ticket):
+        c = np.zeros(4, np.int64)
+        _capi.check(self._lib.tsdf_grid_stats_wait(self._handle, int(ticket), _capi.ptr(c)))
+        return dict(updated_last=int(c[0]), updated_total=int(c[1]), bricks_visited_last=int(c[2]),
+                    frames=int(c[3]))
+
     def sync(self):
         _capi.check(self._lib.tsdf_grid_sync(self._handle))
 

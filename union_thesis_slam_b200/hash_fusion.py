@@ -163,12 +163,16 @@ class HashTable:
         _capi.check(self._lib.vh_remove_blocks(self._handle, _capi.ptr(keys), len(keys), C.byref(removed)))
         return removed.value
 
-    # -- per-voxel container API (reference hash_fusion.py:192-440) --------------------------------
-    # The reference keeps one entry per voxel in 5-slot buckets with offset chains and exposes that
-    # container directly (its tests/hash_map_test.py drives it).  Here integrate() stores 8^3 blocks
-    # in the lock-free block table; the reference-layout container is a second device structure
-    # (bucket_table.VoxelBucketTable, csrc/bucket_kernels.cu) of `map_size` buckets that these
-    # calls operate on.  Once it has been used, the occupancy metrics below describe it.
+    # -- per-voxel API (reference hash_fusion.py:192-440) -------------------------------------------
+    # The reference keeps one entry per voxel in 5-slot buckets with offset chains, fills it from
+    # integrate() and exposes it directly (its tests/hash_map_test.py drives add / get / remove by hand).
+    # Here integrate() stores 8^3 blocks in the lock-free block table, and the per-voxel calls see ONE
+    # map made of two stores:
+    #   * voxels written by integrate(): answered from the block table (vh_voxel_query) -- a voxel has an
+    #     entry iff its weight is > 0, exactly when the reference would have created one;
+    #   * entries added by hand (add_hash_entry / add_voxel): the reference-layout bucket container
+    #     (bucket_table.VoxelBucketTable, csrc/bucket_kernels.cu), created by the first such call.
+    # Look-ups never create the container, so they do not change what the occupancy metrics report.
     @property
     def voxel_table(self):
         if self._voxels is None:
@@ -176,20 +180,54 @@ class HashTable:
             self._voxels = bucket_table.VoxelBucketTable(self._map_size, 5, self._load_factor, self.device)
         return self._voxels
 
+    def _block_query(self, coords, remove=False):
+        """(found bool[n], values float32[n,3] = sdf, weight, colour) of voxel coordinates in the block map."""
+        q = np.ascontiguousarray(np.asarray(coords).reshape(-1, 3), dtype=np.int32)
+        out = np.empty((len(q), 3), np.float32)
+        found = np.zeros(len(q), np.uint8)
+        _capi.check(self._lib.vh_voxel_query(self._handle, _capi.ptr(q), len(q), 1 if remove else 0,
+                                              _capi.ptr(out), _capi.ptr(found)))
+        return found.astype(bool), out
+
+    def query_voxels(self, coords):
+        """Batch form of get_voxel for voxels written by integrate(): (found, sdf, weight, colour) arrays."""
+        found, out = self._block_query(coords)
+        return found, out[:, 0], out[:, 1], out[:, 2]
+
     def add_voxel(self, voxel, world_coord):
         self.voxel_table.add_voxel(voxel, world_coord)
 
     def add_hash_entry(self, hash_entry):
         return self.voxel_table.add_hash_entry(hash_entry)
 
-    def get_voxel(self, world_coord):
-        return self.voxel_table.get_voxel(world_coord)
-
     def get_hash_entry(self, world_coord):
-        return self.voxel_table.get_hash_entry(world_coord)
+        """The entry of a voxel coordinate or None (reference hash_fusion.py:285-310).  Entries are
+        snapshots: the map itself lives on the device."""
+        if self._voxels is not None or self._per_voxel:
+            e = self.voxel_table.get_hash_entry(world_coord)
+            if e is not None or self._per_voxel:
+                return e
+        found, out = self._block_query(world_coord)
+        if not found[0]:
+            return None
+        from . import bucket_table
+        pos = [int(v) for v in np.asarray(world_coord).reshape(-1)[:3]]
+        return bucket_table.HashEntry(pos, None, bucket_table.Voxel(float(out[0, 0]), float(out[0, 2]), float(out[0, 1])))
+
+    def get_voxel(self, world_coord):
+        """The voxel of a coordinate, or None when it has no entry (the reference raises AttributeError
+        on None here, hash_fusion.py:312-320; returning None is the usable form of the same answer)."""
+        e = self.get_hash_entry(world_coord)
+        return None if e is None else e.get_voxel()
 
     def remove(self, world_coord):
-        self.voxel_table.remove(world_coord)
+        """Removes the voxel's entry (reference hash_fusion.py:322-329): a hand-added container entry if
+        there is one, else the voxel written by integrate() goes back to the no-entry state."""
+        if self._voxels is not None or self._per_voxel:
+            if self._per_voxel or self.voxel_table.get_hash_entry(world_coord) is not None:
+                self.voxel_table.remove(world_coord)
+                return
+        self._block_query(world_coord, remove=True)
 
     def remove_hash_entry(self, hash_entry):
         return self.voxel_table.remove_hash_entry(hash_entry)
@@ -198,23 +236,45 @@ class HashTable:
         self.voxel_table.double_table_size()
 
     def get_num_collisions(self):
-        return self.voxel_table.get_num_collisions()
+        return self.voxel_table.get_num_collisions() if (self._voxels is not None or self._per_voxel) else 0
+
+    def count_voxels(self):
+        """Voxels with an entry among those written by integrate() (weight > 0), counted on the device."""
+        n = C.c_int64()
+        _capi.check(self._lib.vh_count_voxels(self._handle, C.byref(n)))
+        return n.value
 
     # -- occupancy metrics (reference hash_fusion.py:147-180) ------------------------------------
+    _STAT_NAMES = ["blocks", "table_keys", "table_slots", "heap_capacity", "heap_free", "updated_last",
+                   "updated_total", "blocks_visited_last", "max_probe", "keys_inserted_last", "frames",
+                   "candidates_last"]
+
     def stats(self):
         s = np.zeros(12, np.int64)
         _capi.check(self._lib.vh_stats(self._handle, _capi.ptr(s)))
-        names = ["blocks", "table_keys", "table_slots", "heap_capacity", "heap_free", "updated_last",
-                 "updated_total", "blocks_visited_last", "max_probe", "keys_inserted_last", "frames",
-                 "candidates_last"]
-        return {k: int(v) for k, v in zip(names, s)}
+        return {k: int(v) for k, v in zip(self._STAT_NAMES, s)}
+
+    def stats_post(self):
+        """Non-blocking stats (vh_stats_post): returns a ticket for stats_wait()."""
+        t = C.c_int64()
+        _capi.check(self._lib.vh_stats_post(self._handle, C.byref(t)))
+        return t.value
+
+    def stats_wait(self, ticket):
+        s = np.zeros(12, np.int64)
+        _capi.check(self._lib.vh_stats_wait(self._handle, int(ticket), _capi.ptr(s)))
+        return {k: int(v) for k, v in zip(self._STAT_NAMES, s)}
 
     def count_num_hash_entries(self):
-        """Number of stored entries: voxel entries of the per-voxel container once that is in use,
-        else allocated 8^3 blocks."""
+        """Number of voxel entries, the reference's unit (hash_fusion.py:147-154): voxels written by
+        integrate() that have weight > 0 plus entries added by hand.  ``stats()["blocks"]`` is the
+        number of 8^3 blocks that hold them."""
+        if self._per_voxel:
+            return self.voxel_table.count_num_hash_entries()
+        n = self.count_voxels()
         if self._voxels is not None:
-            return self._voxels.count_num_hash_entries()
-        return self.stats()["blocks"]
+            n += self._voxels.count_num_hash_entries()
+        return n
 
     def get_num_non_empty_bucket(self):
         if self._voxels is not None:
