@@ -93,7 +93,9 @@ int tsdf_grid_stats(tsdf_grid *g, int64_t counters[4]);
  * wait() blocks until THAT snapshot has landed -- not until the device is idle -- and returns it.  A
  * caller that integrates frame k, posts, and then reads the ticket of frame k-1 gets every frame's
  * result while the upload of frame k+1 overlaps the integration of frame k (the reference's loop,
- * grid_demo1.py:76-87, has no per-frame read-back at all).  The last 16 tickets stay readable. */
+ * grid_demo1.py:76-87, has no per-frame read-back at all).  The last 16 tickets stay readable.
+ * counters[1] (running total) is -1 in a snapshot: later frames may already be adding to it;
+ * tsdf_grid_stats reports it. */
 int tsdf_grid_stats_post(tsdf_grid *g, int64_t *ticket);
 int tsdf_grid_stats_wait(tsdf_grid *g, int64_t ticket, int64_t counters[4]);
 int tsdf_grid_sync(tsdf_grid *g);

@@ -221,3 +221,24 @@ def test_camera_inside_volume_near_plane_voxels():
         n = orc.integrate(c, d, case["K"], p, obs_weight=obs)
         assert vol.stats()["updated_last"] == n
     assert_parity(_state(vol), (orc._tsdf_vol_cpu, orc._weight_vol_cpu, orc._color_vol_cpu))
+
+
+def test_pipelined_stats_snapshots_match_per_frame_counts():
+    """stats_post()/stats_wait(): every frame's counters read without idling the device -- the snapshot
+    of frame k taken while later frames are already queued equals the oracle's per-frame update count."""
+    from union_thesis_slam_b200 import _capi
+    case = scenes.small_case(108, dims=(50, 48, 52), voxel_size=0.02, nframes=20)
+    vol = _gpu_volume(case["vol_bnds"].copy(), 0.02)
+    orc = oracle.OracleTSDFVolume(case["vol_bnds"].copy(), 0.02)
+    tickets, want = [], []
+    for c, d, p, obs in case["frames"]:
+        vol.integrate(c, d, case["K"], p, obs_weight=obs)
+        tickets.append(vol.stats_post())
+        want.append(orc.integrate(c, d, case["K"], p, obs_weight=obs))
+    got = [vol.stats_wait(t) for t in tickets[-16:]]
+    assert [g["updated_last"] for g in got] == want[-16:]
+    assert [g["frames"] for g in got] == list(range(5, 21))
+    with pytest.raises(_capi.TSDFError):
+        vol.stats_wait(tickets[0])  # only the last 16 snapshots are kept
+    assert vol.stats()["updated_total"] == sum(want)
+    assert_parity(_state(vol), (orc._tsdf_vol_cpu, orc._weight_vol_cpu, orc._color_vol_cpu))

@@ -151,6 +151,8 @@ int FrameIO::init()
         }
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stat, cudaStreamNonBlocking));
+    for (int i = 0; i < FRAME_SLOTS; ++i) CUDA_TRY(cudaEventCreateWithFlags(&stat_done[i], cudaEventDisableTiming));
     {   // preparation kernels are short and on the critical path of the next frame: highest priority
         int lo = 0, hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -370,6 +372,7 @@ int FrameIO::begin_kernels()
     // the integrate kernels of the frame FRAME_SLOTS calls ago were the last readers of this slot
     CUDA_TRY(cudaStreamWaitEvent(pre, int_done[slot], 0));
     for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
+    if (stat_used) CUDA_TRY(cudaStreamWaitEvent(pre, stat_done[slot], 0)); // a counter snapshot may still read the slot
     if (timing) CUDA_TRY(cudaEventRecord(k_begin, pre));
     CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
     n_marks = 0;
@@ -381,6 +384,20 @@ int FrameIO::prepared()
     CUDA_TRY(cudaEventRecord(pre_done[slot], pre));
     CUDA_TRY(cudaStreamWaitEvent(compute, pre_done[slot], 0));
     for (int k = 0; k < n_side; ++k) CUDA_TRY(cudaStreamWaitEvent(side[k], pre_done[slot], 0));
+    return TSDF_OK;
+}
+
+int FrameIO::stat_begin()
+{
+    CUDA_TRY(cudaStreamWaitEvent(stat, int_done[slot], 0));
+    for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(stat, side_int_done[k][slot], 0));
+    return TSDF_OK;
+}
+
+int FrameIO::stat_end()
+{
+    CUDA_TRY(cudaEventRecord(stat_done[slot], stat));
+    stat_used = true;
     return TSDF_OK;
 }
 
@@ -467,7 +484,9 @@ void FrameIO::release()
     if (compute) cudaStreamSynchronize(compute);
     sync_side();
     if (copy) cudaStreamSynchronize(copy);
+    if (stat) cudaStreamSynchronize(stat);
     for (int i = 0; i < FRAME_SLOTS; ++i) {
+        if (stat_done[i]) cudaEventDestroy(stat_done[i]);
         for (int k = 0; k < MAX_SIDE; ++k) {
             if (side_int_done[k][i]) cudaEventDestroy(side_int_done[k][i]);
             if (side_slot_free[k][i]) cudaEventDestroy(side_slot_free[k][i]);
@@ -496,6 +515,7 @@ void FrameIO::release()
         if (side[k]) cudaStreamDestroy(side[k]);
     }
     if (copy) cudaStreamDestroy(copy);
+    if (stat) cudaStreamDestroy(stat);
     if (pre) cudaStreamDestroy(pre);
 }
 
@@ -520,7 +540,7 @@ int CounterStore::post(int slot, const FrameScratch *fs, const Totals *tot, cons
                        cudaStream_t s, int64_t frames, int64_t *ticket)
 {
     const int r = (int)(next_ticket % STATS_RING);
-    launch_collect_stats(view(slot), n, fs, tot, n_entries, heap_top, d_ring + r, s);
+    launch_collect_stats(view(slot), n, fs, tot, n_entries, heap_top, d_ring + r, s, false);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_ring + r, d_ring + r, sizeof(StatsBlock), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(ring_done[r], s));
@@ -899,9 +919,10 @@ extern "C" int tsdf_grid_stats_post(tsdf_grid *g, int64_t *ticket)
     BAD_ARG(!g || !ticket, "NULL argument");
     CUDA_TRY(cudaSetDevice(g->device));
     int rc = grid_flush_batch(g);
-    if (rc || (rc = g->io.join())) return rc;
+    if (rc || (rc = g->io.stat_begin())) return rc;
     const int slot = g->frames > 0 ? g->io.slot : 0;
-    return g->counters.post(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.compute, g->frames, ticket);
+    if ((rc = g->counters.post(slot, g->io.fs, g->tot, nullptr, nullptr, g->io.stat, g->frames, ticket))) return rc;
+    return g->io.stat_end();
 }
 
 extern "C" int tsdf_grid_stats_wait(tsdf_grid *g, int64_t ticket, int64_t counters[4])
@@ -913,7 +934,7 @@ extern "C" int tsdf_grid_stats_wait(tsdf_grid *g, int64_t ticket, int64_t counte
     int rc = g->counters.wait(ticket, &st, &frames);
     if (rc) return rc;
     counters[0] = frames > 0 ? (int64_t)st->updated_last : 0;
-    counters[1] = (int64_t)st->updated_total;
+    counters[1] = -1; // later frames may already be adding to the running total: tsdf_grid_stats has it
     counters[2] = frames > 0 ? (int64_t)st->vis_count : 0;
     counters[3] = frames;
     return TSDF_OK;
@@ -924,6 +945,7 @@ extern "C" int tsdf_grid_sync(tsdf_grid *g)
     BAD_ARG(!g, "NULL handle");
     CUDA_TRY(cudaSetDevice(g->device));
     { int rc_ = grid_flush_batch(g); if (rc_) return rc_; }
+    CUDA_TRY(cudaStreamSynchronize(g->io.stat));
     CUDA_TRY(cudaStreamSynchronize(g->io.copy));
     CUDA_TRY(cudaStreamSynchronize(g->io.pre));
     CUDA_TRY(cudaStreamSynchronize(g->io.compute));

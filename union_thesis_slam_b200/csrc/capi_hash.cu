@@ -5,6 +5,7 @@
 
 #include "host_common.h"
 
+#define WALK_SB_PER_TILE 400.0 // the scan still wins at 83 super-blocks per tile (16x the scene's bounds, profiles/r2_hash_alloc.md)
 struct tsdf_hash {
     int device = 0, sm_count = 0, rank = 0, world = 1;
     VolumeGeom geom;
@@ -26,7 +27,13 @@ struct tsdf_hash {
     // true: K2's cone walk per pixel tile flags them first (cost scales with pixels x depth).
     // Both are conservative and K3's per-block test decides, so the allocated set is identical;
     // TSDF_HASH_ALLOC=walk|grid overrides the default for measurement (profiles/r1_hash_alloc.md).
-    bool ray_walk = false;
+    // Allocation front end: which 32^3-voxel super-blocks can the frame touch?
+    //   grid (0): one warp per super-block of the bounded volume tests it against the frame (cost ~ volume)
+    //   walk (1): the per-pixel-tile cone walk flags them (cost ~ pixels x depth)
+    //   auto (2, default): per frame, whichever the cost model below says is cheaper -- the walk once the
+    //   bounded volume holds more than WALK_SB_PER_TILE super-blocks per 8x8-pixel tile
+    //   (profiles/r2_hash_alloc.md).  TSDF_HASH_ALLOC=grid|walk|auto overrides.
+    int alloc_mode = 2;
 };
 
 static int hash_free(tsdf_hash *h)
@@ -72,7 +79,15 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
             tsdf_set_error("volume has too many blocks along axis %d (limit 32767)", a);
             return TSDF_ERR_BAD_ARG;
         }
-    if (const char *e = getenv("TSDF_HASH_ALLOC")) h->ray_walk = strcmp(e, "walk") == 0;
+    // the presence bitmap, the super-block flags and the launch grids index the bounded block grid with
+    // 32-bit integers: a wrapped index would alias `known` bits and silently drop allocations
+    if ((int64_t)h->geom.nb[0] * h->geom.nb[1] * h->geom.nb[2] >= ((int64_t)1 << 31)) {
+        const long long nblk = (long long)h->geom.nb[0] * h->geom.nb[1] * h->geom.nb[2];
+        hash_free(h);
+        tsdf_set_error("bounded volume holds %lld blocks (limit 2^31 - 1): use a coarser voxel size or smaller bounds", nblk);
+        return TSDF_ERR_BAD_ARG;
+    }
+    if (const char *e = getenv("TSDF_HASH_ALLOC")) h->alloc_mode = !strcmp(e, "walk") ? 1 : (!strcmp(e, "grid") ? 0 : 2);
     int64_t S = 1024;
     while (S < table_slots) S <<= 1;
     h->table_slots = S;
@@ -206,12 +221,14 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     cudaStream_t s = h->io.pre;
     launch_prep_frame(d_rgb, d_depth, h->io.d_px, h->io.fs, h->io.pyr, H, W, s);
     CUDA_TRY(cudaGetLastError());
-    if (h->ray_walk) {
+    const double n_sb = (double)h->dev.nsx * h->dev.nsy * h->dev.nsz;
+    const bool ray_walk = h->alloc_mode == 1 || (h->alloc_mode == 2 && n_sb > WALK_SB_PER_TILE * tiles_x * tiles_y);
+    if (ray_walk) {
         CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
         launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
         CUDA_TRY(cudaGetLastError());
     }
-    launch_refine_insert(f, c, h->dev, h->ray_walk ? h->sb_flags : nullptr, h->io.fs, h->tot, s);
+    launch_refine_insert(f, c, h->dev, ray_walk ? h->sb_flags : nullptr, h->io.fs, h->tot, s);
     CUDA_TRY(cudaGetLastError());
     // a key exists at most once per block of the bounded grid: bound the scan by that, not by the table size
     launch_compact_visible(f, c, h->dev, (int)std::min<int64_t>(h->table_slots, (int64_t)h->dev.nbx * h->dev.nby * h->dev.nbz),
@@ -282,7 +299,7 @@ static int hash_fill_stats(tsdf_hash *h, const StatsBlock *st, int64_t frames, i
     stats[3] = h->heap_blocks;
     stats[4] = st->heap_top;
     stats[5] = frames > 0 ? (int64_t)st->updated_last : 0;
-    stats[6] = (int64_t)st->updated_total;
+    stats[6] = st->updated_total == ~0ull ? -1 : (int64_t)st->updated_total; // -1 in asynchronous snapshots
     stats[7] = (int64_t)st->last_visited;
     stats[8] = (int64_t)st->max_probe;
     stats[9] = st->new_keys;
@@ -315,7 +332,10 @@ extern "C" int vh_stats_post(tsdf_hash *h, int64_t *ticket)
     BAD_ARG(!h || !ticket, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     const int slot = h->frames > 0 ? h->io.slot : 0;
-    return h->counters.post(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.compute, h->frames, ticket);
+    int rc = h->io.stat_begin();
+    if (rc || (rc = h->counters.post(slot, h->io.fs, h->tot, h->dev.n_entries, h->dev.heap_top, h->io.stat, h->frames, ticket)))
+        return rc;
+    return h->io.stat_end();
 }
 
 extern "C" int vh_stats_wait(tsdf_hash *h, int64_t ticket, int64_t stats[12])
@@ -342,6 +362,7 @@ extern "C" int vh_sync(tsdf_hash *h)
 {
     BAD_ARG(!h, "NULL handle");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->io.stat));
     CUDA_TRY(cudaStreamSynchronize(h->io.copy));
     CUDA_TRY(cudaStreamSynchronize(h->io.pre));
     CUDA_TRY(cudaStreamSynchronize(h->io.compute));

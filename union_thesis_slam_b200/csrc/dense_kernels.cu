@@ -343,13 +343,13 @@ k_integrate_dense_v1(FrameParams f, VolumeParams v, const BrickRef *__restrict__
 
 // Stats read-out: sums the per-warp update counters and gathers the scalar counters into one block.
 __global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot,
-                                const int *n_entries, const int *heap_top, StatsBlock *out)
+                                const int *n_entries, const int *heap_top, StatsBlock *out, int with_total)
 {
     __shared__ unsigned long long s_a[8], s_b[8];
     unsigned long long a = 0, b = 0;
     for (int i = threadIdx.x; i < n_warps; i += blockDim.x) {
         a += uc.frame[i];
-        b += uc.total[i];
+        if (with_total) b += uc.total[i]; // not for snapshots taken while later frames run (they add to total[])
     }
     for (int o = 16; o; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -361,7 +361,7 @@ __global__ void k_collect_stats(UpdateCounters uc, int n_warps, const FrameScrat
         a = b = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_a[i]; b += s_b[i]; }
         StatsBlock r;
-        r.updated_last = a; r.updated_total = b;
+        r.updated_last = a; r.updated_total = with_total ? b : ~0ull;
         r.last_visited = tot->last_visited; r.max_probe = tot->max_probe; r.error = tot->error;
         r.cand_count = fs ? fs->cand_count : 0; r.new_keys = fs ? fs->new_keys : 0;
         r.vis_count = fs ? fs->vis_count + fs->vis_extra[0] + fs->vis_extra[1] + fs->vis_extra[2] : 0;
@@ -440,9 +440,9 @@ void launch_cull_bricks_batch(const FrameParams *f, const CullParams *c, FrameSc
 int integrate_reserve_ctas() { return INTEGRATE_RESERVE_CTAS; }
 
 void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
-                          const int *heap_top, StatsBlock *out, cudaStream_t s)
+                          const int *heap_top, StatsBlock *out, cudaStream_t s, bool with_total)
 {
-    k_collect_stats<<<1, 256, 0, s>>>(uc, n_warps, fs, tot, n_entries, heap_top, out);
+    k_collect_stats<<<1, 256, 0, s>>>(uc, n_warps, fs, tot, n_entries, heap_top, out, with_total ? 1 : 0);
 }
 
 int integrate_dense_ctas_per_sm()

@@ -92,6 +92,13 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
 //    chain is three dependent launches; with two slots it sat on the critical path of short frames).
 struct FrameIO {
     cudaStream_t compute = nullptr, copy = nullptr, pre = nullptr;
+    // Snapshots of the counters (stats_post) are taken on their own stream behind the frame's integrate
+    // events, so that they never order one frame's kernels before the next one's.
+    cudaStream_t stat = nullptr;
+    cudaEvent_t stat_done[FRAME_SLOTS] = {};
+    bool stat_used = false;
+    int stat_begin();  // `stat` waits for the integrate kernels of the last frame issued
+    int stat_end();    // marks the snapshot's reads of the frame slot as done (the slot's next user waits for it)
     // sibling integrate streams of the dense grid (independent classes of bricks, see k_cull_bricks);
     // n_side is set by the handle: how many of them the frame being issued uses (0: all on `compute`)
     static const int MAX_SIDE = DENSE_MAX_CLASSES - 1;

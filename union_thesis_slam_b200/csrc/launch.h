@@ -61,7 +61,7 @@ void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int
                         int classes, BrickRef *lists, size_t class_cap, FrameScratch *fs, cudaStream_t s);
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
 void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs, const Totals *tot, const int *n_entries,
-                          const int *heap_top, StatsBlock *out, cudaStream_t s);
+                          const int *heap_top, StatsBlock *out, cudaStream_t s, bool with_total = true);
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
