@@ -310,7 +310,7 @@ def workload_config(world):
                         "(1000x1000x400 = 4.0e8 voxels, 4.8 GB), 640x480 frames, seeded trajectory",
             "voxel_size_m": VOXEL, "grid": [1000, 1000, 400], "image": [IM_W, IM_H],
             "frames_resident": N_FRAMES, "obs_weight": 1.0,
-            "partition": "cyclic brick-thick x-sheets, rank = sheet %% %d" % world,
+            "partition": "brick-thick x-sheets dealt to %d rank(s) in snake order" % world,
             "l2_policy": "working set (4.8 GB voxel state, 2-4 GB touched per frame) exceeds the 126 MB L2"}
 
 

@@ -37,14 +37,26 @@ def _spawn(fn, world=2):
     return dict(ret)
 
 
-def test_owned_x_is_a_partition_with_brick_thick_cyclic_sheets():
-    for dim_x, world in [(405, 2), (405, 8), (1000, 4), (7, 3), (64, 8)]:
+def test_owned_x_is_a_partition_with_brick_thick_snake_dealt_sheets():
+    for dim_x, world in [(405, 2), (405, 8), (1000, 4), (7, 3), (64, 8), (100, 1)]:
         seen = np.zeros(dim_x, int)
         for r in range(world):
             xs = tdist.owned_x(dim_x, r, world)
-            assert np.all((xs // 8) % world == r) and np.all(np.diff(xs) > 0)
+            m = (xs // 8) % (2 * world)   # snake: 0 1 .. W-1 W-1 .. 1 0
+            assert np.all(np.where(m < world, m, 2 * world - 1 - m) == r) and np.all(np.diff(xs) > 0)
             seen[xs] += 1
         assert np.all(seen == 1)
+
+
+def test_snake_dealing_cancels_a_linear_load_trend():
+    """What the snake order is for: a load that grows linearly along x (a frustum's cross-section) splits evenly."""
+    world, sheets = 8, 128
+    load = 10.0 + np.arange(sheets)
+    owner = tdist.sheet_owner(np.arange(sheets), world)
+    per_rank = np.bincount(owner, weights=load, minlength=world)
+    assert per_rank.max() / per_rank.mean() < 1.001
+    round_robin = np.bincount(np.arange(sheets) % world, weights=load, minlength=world)
+    assert round_robin.max() / round_robin.mean() > 1.04
 
 
 def test_block_owner_is_balanced_and_decorrelated_from_slot_hash():

@@ -670,10 +670,10 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
         return rc;
     }
     const int nbx = g->geom.nb[0];
-    g->nlbx = nbx > rank ? (nbx - rank + world - 1) / world : 0;
+    g->nlbx = sheets_of(nbx, rank, world);
     g->n_x_local = 0;
     for (int l = 0; l < g->nlbx; ++l) {
-        const int64_t x0 = (int64_t)(l * world + rank) * BRICK;
+        const int64_t x0 = (int64_t)sheet_of(l, rank, world) * BRICK;
         g->n_x_local += std::min<int64_t>(BRICK, dim[0] - x0);
     }
     g->nbricks = (size_t)g->nlbx * g->geom.nb[1] * g->geom.nb[2];
@@ -848,7 +848,7 @@ extern "C" int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs)
     if (xs) {
         int64_t k = 0;
         for (int l = 0; l < g->nlbx; ++l) {
-            const int64_t x0 = (int64_t)(l * g->world + g->rank) * BRICK;
+            const int64_t x0 = (int64_t)sheet_of(l, g->rank, g->world) * BRICK;
             for (int64_t x = x0; x < std::min<int64_t>(x0 + BRICK, g->geom.dim[0]); ++x) xs[k++] = x;
         }
     }

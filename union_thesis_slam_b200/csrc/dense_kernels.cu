@@ -97,7 +97,7 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
         bz = i % nbz;
         by = (i / nbz) % nby;
         const int lbx = i / (nbz * nby);
-        bx = lbx * world + rank;
+        bx = sheet_of(lbx, rank, world);
         cls = (lbx + by + bz) % classes;
         c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
         vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
@@ -139,7 +139,7 @@ __global__ void k_cull_bricks_batch(CullBatch cb, int nlbx, int nby, int nbz, in
         bz = i % nbz;
         by = (i / nbz) % nby;
         const int lbx = i / (nbz * nby);
-        bx = lbx * world + rank;
+        bx = sheet_of(lbx, rank, world);
         cls = (lbx + by + bz) % classes;
 #pragma unroll 1
         for (int k = 0; k < cb.n; ++k) {

@@ -20,6 +20,25 @@ struct FrameScratch {
     int vis_extra[3];            // dense: entries in the visible-brick lists of brick classes 1..3
     int pad;
 };
+// Dense grid sharding: brick-thick x-sheets dealt to the ranks in SNAKE order (0 1 .. W-1 W-1 .. 1 0 0 1 ..).
+// A frustum's load per sheet changes smoothly along x; plain round-robin hands rank W-1 every sheet's
+// "later" neighbour, which adds up to a 7-8 % per-frame imbalance at 8 ranks, while the snake pairs each
+// rank's sheets so that a linear trend cancels.  sheet_of(): global sheet of rank's l-th local sheet;
+// sheets_of(): how many sheets of nbx the rank owns.  dist.owned_x() is the Python mirror.
+#ifdef __CUDACC__
+#define TSDF_HD __host__ __device__
+#else
+#define TSDF_HD
+#endif
+static inline TSDF_HD int sheet_of(int l, int rank, int world)
+{
+    return 2 * world * (l >> 1) + ((l & 1) ? 2 * world - 1 - rank : rank);
+}
+static inline int sheets_of(int nbx, int rank, int world)
+{
+    const int period = 2 * world, full = nbx / period, rem = nbx % period;
+    return 2 * full + (rank < rem ? 1 : 0) + (period - 1 - rank < rem ? 1 : 0);
+}
 #define DENSE_MAX_CLASSES 4
 #define DENSE_MAX_BATCH 4 // frames applied to a brick in one visit (temporal blocking)
 

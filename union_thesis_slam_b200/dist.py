@@ -31,10 +31,18 @@ def local_device(device=None):
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def sheet_owner(sheet, world):
+    """Owner of brick-thick x-sheet(s): the sheets are dealt in snake order (0 1 .. W-1 W-1 .. 1 0 0 1 ..), which
+    cancels the linear trend of a frustum's load along x that plain round-robin turns into a 7-8 % per-frame
+    imbalance at 8 ranks.  Mirrors sheet_of() in csrc/launch.h."""
+    m = np.asarray(sheet, dtype=np.int64) % (2 * world)
+    return np.where(m < world, m, 2 * world - 1 - m)
+
+
 def owned_x(dim_x, rank, world):
-    """Global x indices (voxels) of the brick-thick x-sheets rank owns: sheet s -> rank s % world."""
+    """Global x indices (voxels) of the brick-thick x-sheets rank owns, ascending."""
     x = np.arange(int(dim_x), dtype=np.int64)
-    return x[(x // BRICK) % world == rank]
+    return x[sheet_owner(x // BRICK, world) == rank]
 
 
 def block_owner(keys, world):

@@ -6,7 +6,7 @@ behind the C ABI in include/tsdf_b200.h (csrc/dense_kernels.cu).  Results follow
 CPU path (numba branch, grid_fusion.py:260-314) bit for bit; there is no CPU fallback.
 
 Multi-GPU: one process per GPU.  With an initialised ``torch.distributed`` group (or explicit
-``rank`` / ``world_size``) each process owns the brick-thick x-sheets ``s % world == rank``;
+``rank`` / ``world_size``) each process owns the brick-thick x-sheets dealt to it in snake order (dist.sheet_owner);
 ``integrate`` needs no communication and ``get_volume`` gathers over NCCL.
 """
 import ctypes as C
