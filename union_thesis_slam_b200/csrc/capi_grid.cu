@@ -625,8 +625,6 @@ struct tsdf_grid {
     bool unit_w = true; // every frame so far had obs_weight == 1 (weights are integers)
     // Temporal blocking: up to `batch` consecutive frames are prepared as they arrive and applied to
     // every brick in ONE visit (tsdf_grid_set_batch).  q_* is the batch being collected.
-    // small shards: quad layers instead of whole bricks as the persistent grid's work unit (see k_integrate_dense_v1)
-    bool half_units = false;
     int batch = 1;
     int q_n = 0;
     FrameParams q_f[DENSE_MAX_BATCH];
@@ -708,8 +706,6 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     // next frame's preparation kernels (other stream) can run beside it
     g->integrate_grid = sm * std::max(1, integrate_dense_ctas_per_sm() - integrate_reserve_ctas());
     if (const char *e = getenv("TSDF_DENSE_CTAS_PER_SM")) g->integrate_grid = sm * std::min(32, std::max(1, atoi(e)));
-    // measured slower at every shard size (profiles/r2_dense_ab.md): off unless asked for
-    if (const char *e = getenv("TSDF_DENSE_HALF_UNITS")) g->half_units = atoi(e) != 0;
     if ((rc = g->counters.init(g->classes * g->integrate_grid * (INTEGRATE_THREADS / 32)))) {
         grid_free(g);
         return rc;
@@ -755,7 +751,7 @@ static int grid_flush_batch(tsdf_grid *g)
         cudaStream_t st = (c && g->io.n_side) ? g->io.side[c - 1] : g->io.compute;
         if (k == 1)
             launch_integrate_dense(g->q_f[0], vp, list + c * g->class_cap, count, g->bricks,
-                                   g->counters.view(g->io.slot, c * warps), g->integrate_grid, st, g->half_units);
+                                   g->counters.view(g->io.slot, c * warps), g->integrate_grid, st);
         else
             launch_integrate_dense_batch(g->q_f, k, vp, list + c * g->class_cap, count, g->bricks,
                                          g->counters.view(g->io.slot, c * warps), g->integrate_grid, st);

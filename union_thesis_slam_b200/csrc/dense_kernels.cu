@@ -306,10 +306,10 @@ k_integrate_dense(FrameBatch<K> fb, VolumeParams v, const BrickRef *__restrict__
     }
 }
 
-// HALF = true: the work unit is one QUAD LAYER of a brick (4 of its 8 z-levels) instead of a whole brick:
-// twice as many, half as long units.  Used for small shards (few list entries per resident CTA), where the
-// last round of whole bricks leaves most of the persistent grid idle (profiles/r2_scaling.md).
-template <bool UNIT_W, bool HALF>
+// (Quad layers instead of whole bricks as the work unit -- for every brick, or only for the bricks of the last,
+// partial round of a launch -- were measured at 1 / 2 / 4 / 8 ranks and changed nothing or lost: the second
+// class's launch already fills a launch's tail.  profiles/r2_dense_ab.md.)
+template <bool UNIT_W>
 __global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
 k_integrate_dense_v1(FrameParams f, VolumeParams v, const BrickRef *__restrict__ list, const int *__restrict__ count,
                      float *__restrict__ bricks, UpdateCounters uc, int n_sm)
@@ -317,24 +317,22 @@ k_integrate_dense_v1(FrameParams f, VolumeParams v, const BrickRef *__restrict__
     // per-thread update counter in shared memory: a fire-and-forget add per column instead of a register
     // that the 64-register budget would spill (its reload sat on the long scoreboard)
     __shared__ unsigned s_updates[INTEGRATE_THREADS];
-    const int n = HALF ? 2 * *count : *count;
+    const int n = *count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
     s_updates[t] = 0; // only this thread touches its counter: no barrier needed
     int round = 0;
     int b = entry_of(0, n_sm);
     int4 br_next = make_int4(0, 0, 0, 0);
-    if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + (HALF ? b >> 1 : b));
+    if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
     while (b < n) {
         const int4 br = br_next;
-        const int h0 = HALF ? (b & 1) : 0;
         b = entry_of(++round, n_sm);
-        if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + (HALF ? b >> 1 : b));
+        if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
         const int gx = br.x * BRICK + lx, gy = br.y * BRICK + ly;
         if (gx >= v.dim_x || gy >= v.dim_y) continue;
         const unsigned nupd = integrate_column8<UNIT_W, false>(f, v, gx, gy, br.z * BRICK,
-                                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t, h0,
-                                                                HALF ? h0 + 1 : 2);
+                                                                bricks + (size_t)(uint32_t)br.w * BRICK_FLOATS + 8 * t);
         if (nupd) atomicAdd(&s_updates[t], nupd);
     }
     unsigned my_updates = s_updates[t];
@@ -453,7 +451,7 @@ void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs
 int integrate_dense_ctas_per_sm()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense_v1<true, false>, INTEGRATE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_integrate_dense_v1<true>, INTEGRATE_THREADS, 0);
     return n > 0 ? n : 1;
 }
 
@@ -495,21 +493,14 @@ static void launch_batch(const FrameParams *f, const VolumeParams &v, const Bric
 }
 
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
-                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s, bool half_units)
+                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s)
 {
     if (dense_v1()) {
         const int sms = sm_count_for(grid);
-        if (half_units) {
-            if (f.unit_w)
-                k_integrate_dense_v1<true, true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
-            else
-                k_integrate_dense_v1<false, true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
-        } else {
-            if (f.unit_w)
-                k_integrate_dense_v1<true, false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
-            else
-                k_integrate_dense_v1<false, false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
-        }
+        if (f.unit_w)
+            k_integrate_dense_v1<true><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
+        else
+            k_integrate_dense_v1<false><<<grid, INTEGRATE_THREADS, 0, s>>>(f, v, list, count, bricks, uc, sms);
         return;
     }
     launch_batch<1>(&f, v, list, count, bricks, uc, grid, s, f.unit_w != 0);

@@ -244,18 +244,18 @@ __device__ __forceinline__ void column_sums(const FrameParams &f, double wx, dou
     cYs = __fma_rn(f.sT[5], wy, __fma_rn(f.sT[4], wx, f.sT[7]));
 }
 
-// One (x, y) column of a brick: 8 voxels as two quads (h = 0, 1), record in global memory; [h0, h1) selects
-// the quads to do (both by default).  Returns the number of voxels updated.
+// One (x, y) column of a brick: 8 voxels as two quads, record in global memory.  Returns the number of
+// voxels updated.
 template <bool UNIT_W, bool PROBE>
 __device__ __forceinline__ unsigned integrate_column8(const FrameParams &f, const VolumeParams &v, int gx, int gy,
-                                                      int gz0, float *rec, int h0 = 0, int h1 = 2)
+                                                      int gz0, float *rec)
 {
     const double wx = __ldg(v.lat_x + gx), wy = __ldg(v.lat_y + gy);
     double cXs, cYs, cZ;
     column_sums(f, wx, wy, cXs, cYs, cZ);
     unsigned n = 0;
 #pragma unroll 1
-    for (int h = h0; h < h1; ++h) {
+    for (int h = 0; h < 2; ++h) {
         const int gz = gz0 + 4 * h;
         const int nvalid = v.dim_z - gz;
         if (nvalid <= 0) break;

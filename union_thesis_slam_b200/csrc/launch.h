@@ -84,7 +84,7 @@ void launch_collect_stats(UpdateCounters uc, int n_warps, const FrameScratch *fs
 int integrate_dense_ctas_per_sm();
 int integrate_reserve_ctas(); // CTA slots per SM left free for the concurrent preparation stream
 void launch_integrate_dense(const FrameParams &f, const VolumeParams &v, const BrickRef *list, const int *count,
-                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s, bool half_units = false);
+                            float *bricks, UpdateCounters uc, int grid, cudaStream_t s);
 void launch_cull_bricks_batch(const FrameParams *f, const CullParams *c, FrameScratch *const *fs, int k, int nlbx, int nby,
                               int nbz, int rank, int world, int classes, BrickRef *lists, size_t class_cap, cudaStream_t s);
 void launch_integrate_dense_batch(const FrameParams *f, int k, const VolumeParams &v, const BrickRef *list,
