@@ -13,4 +13,4 @@ h=d.get("hash",{}); print("hash", h.get("value"), h.get("roofline",{}).get("frac
 for k,v in d.get("configs",{}).items():
     print(k, v if isinstance(v,str) else "%.4g upd/s %.4f ms/frame frac %.3f" % (v["value"], v["ms_per_step"], v["roofline"]["frac"]))
 PY
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 3 --warmup 1 ) 2>&1 | grep -E "impl|real" | cut -c1-400
+[ "${3:-}" = "noref" ] || ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 3 --warmup 1 ) 2>&1 | grep -E "impl|real" | cut -c1-400
