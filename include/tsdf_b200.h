@@ -158,6 +158,14 @@ int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_dept
  * [10] frames integrated, [11] candidate keys emitted by the last frame's ray walk. */
 int vh_stats(tsdf_hash *h, int64_t stats[12]);
 int vh_num_blocks(tsdf_hash *h, int64_t *n);
+/* Block-list read-out for the multi-GPU gather ("read-out = gather of per-rank (keys, voxel payload)
+ * lists"): this rank's blocks into DEVICE buffers -- keys [capacity][3] int32 block coordinates, payload
+ * [capacity][3][512] float32 (tsdf | weight | colour in the float encoding); capacity 0 counts only -- and the
+ * inverse: any block list scattered into dense DEVICE volumes [X][Y][Z] (fill != 0 first writes the defaults
+ * tsdf 1, weight 0, colour 0, hash_fusion.py:447-448).  The caller's torch.distributed exchanges the lists. */
+int vh_export_blocks_device(tsdf_hash *h, int64_t capacity, int64_t *n, int32_t *d_keys, float *d_payload);
+int vh_scatter_blocks_device(tsdf_hash *h, const int32_t *d_keys, const float *d_payload, int64_t n, int fill,
+                             float *d_tsdf, float *d_weight, float *d_color);
 /* Per-voxel view of the block map -- HashTable.get_hash_entry / get_voxel (hash_fusion.py:285-320) and
  * remove (hash_fusion.py:322-393) on the table that integrate() fills.  coords: n voxel indices
  * [n][3]; a voxel has an entry iff its block owns storage and its weight is > 0 (the reference

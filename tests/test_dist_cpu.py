@@ -112,3 +112,49 @@ def _merge_job(rank, world):
 def test_hash_shard_merge_is_bit_exact_world2():
     res = _spawn(_merge_job, 2)
     assert res == {0: [True, True, True], 1: [True, True, True]}
+
+
+def _block_list_job(rank, world):
+    """Hash read-out by block lists: each rank holds the 8^3 blocks it owns (keys + payload), gather_block_lists
+    returns the union on every rank, and scattering it reconstructs the reference volume."""
+    z = np.load(os.path.join(frames.GOLDEN_DIR, "small_dense_11.npz"))
+    t, w, c = z["tsdf"], z["weight"], z["color_vol"]
+    nb = [(s + 7) // 8 for s in t.shape]
+    pad = [n * 8 for n in nb]
+
+    def padded(a, fill):
+        out = np.full(pad, fill, np.float32)
+        out[:a.shape[0], :a.shape[1], :a.shape[2]] = a
+        return out
+
+    pt, pw, pc = padded(t, 1.0), padded(w, 0.0), padded(c, 0.0)
+    keys = np.stack(np.meshgrid(*[np.arange(n) for n in nb], indexing="ij"), -1).reshape(-1, 3)
+    has = np.array([pw[k[0] * 8:k[0] * 8 + 8, k[1] * 8:k[1] * 8 + 8, k[2] * 8:k[2] * 8 + 8].max() > 0 for k in keys])
+    keys = keys[has]                                      # a block exists iff one of its voxels was updated
+    mine = keys[tdist.block_owner(keys, world) == rank]
+    if rank == world - 1:
+        mine = mine[:0] if world > 2 else mine            # world 3: one rank with an empty list
+    payload = np.stack([np.concatenate([p[k[0] * 8:k[0] * 8 + 8, k[1] * 8:k[1] * 8 + 8, k[2] * 8:k[2] * 8 + 8].reshape(-1)
+                                        for p in (pt, pw, pc)]) for k in mine]) if len(mine) else np.zeros((0, 1536), np.float32)
+    gk, gp = tdist.gather_block_lists(torch.from_numpy(mine.astype(np.int32)), torch.from_numpy(payload.astype(np.float32)))
+    gk, gp = gk.numpy(), gp.numpy()
+    ot, ow, oc = np.ones(pad, np.float32), np.zeros(pad, np.float32), np.zeros(pad, np.float32)
+    for k, p in zip(gk, gp):
+        sl = (slice(k[0] * 8, k[0] * 8 + 8), slice(k[1] * 8, k[1] * 8 + 8), slice(k[2] * 8, k[2] * 8 + 8))
+        ot[sl], ow[sl], oc[sl] = p[:512].reshape(8, 8, 8), p[512:1024].reshape(8, 8, 8), p[1024:].reshape(8, 8, 8)
+    cut = tuple(slice(0, s) for s in t.shape)
+    return [len(gk), bool(np.array_equal(ot[cut], t)), bool(np.array_equal(ow[cut], w)), bool(np.array_equal(oc[cut], c)),
+            int(has.sum())]
+
+
+def test_block_list_gather_reconstructs_the_volume_world2():
+    res = _spawn(_block_list_job, 2)
+    for r in (0, 1):
+        n, ok_t, ok_w, ok_c, total = res[r]
+        assert n == total and ok_t and ok_w and ok_c
+
+
+def test_block_list_gather_world3_with_an_empty_rank():
+    res = _spawn(_block_list_job, 3)
+    lens = {res[r][0] for r in range(3)}
+    assert len(lens) == 1 and all(res[r][0] < res[r][4] for r in range(3))  # the last rank's blocks are missing everywhere

@@ -48,6 +48,8 @@ SYMBOLS = [
     ("vh_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("vh_stats", _i, [_p, _p]),
     ("vh_num_blocks", _i, [_p, _p]),
+    ("vh_export_blocks_device", _i, [_p, _i64, _p, _p, _p]),
+    ("vh_scatter_blocks_device", _i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
     ("vh_voxel_query", _i, [_p, _p, _i64, _i, _p, _p]),
     ("vh_count_voxels", _i, [_p, _p]),
     ("vh_stats_post", _i, [_p, _p]),

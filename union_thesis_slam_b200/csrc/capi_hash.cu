@@ -458,6 +458,38 @@ extern "C" int vh_export_blocks(tsdf_hash *h, int64_t capacity, int64_t *n, int3
     return check_device_error(h);
 }
 
+// Block-list read-out for the multi-GPU gather: this rank's blocks into DEVICE buffers (capacity blocks; pass
+// capacity 0 to count), and the inverse -- any block list scattered into dense DEVICE volumes.
+extern "C" int vh_export_blocks_device(tsdf_hash *h, int64_t capacity, int64_t *n, int32_t *d_keys, float *d_payload)
+{
+    BAD_ARG(!h || !n, "NULL argument");
+    BAD_ARG(capacity < 0 || capacity > ((int64_t)1 << 30), "bad capacity");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->io.compute;
+    const bool want = d_keys && d_payload && capacity > 0;
+    CUDA_TRY(cudaMemsetAsync(h->scratch_count, 0, sizeof(int), s));
+    launch_export_blocks(h->dev, want ? (int)capacity : 0, h->scratch_count, d_keys, d_payload, h->sm_count, s);
+    CUDA_TRY(cudaGetLastError());
+    int count = 0;
+    CUDA_TRY(cudaMemcpyAsync(&count, h->scratch_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n = count;
+    return check_device_error(h);
+}
+
+extern "C" int vh_scatter_blocks_device(tsdf_hash *h, const int32_t *d_keys, const float *d_payload, int64_t n, int fill,
+                                        float *d_tsdf, float *d_weight, float *d_color)
+{
+    BAD_ARG(!h || ((!d_keys || !d_payload) && n > 0), "NULL argument");
+    BAD_ARG(n < 0 || n > ((int64_t)1 << 30), "bad block count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    launch_scatter_block_list(d_keys, d_payload, (int)n, (int)h->geom.dim[0], (int)h->geom.dim[1], (int)h->geom.dim[2],
+                              d_tsdf, d_weight, d_color, fill != 0, h->sm_count, h->io.compute);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->io.compute));
+    return TSDF_OK;
+}
+
 extern "C" int vh_remove_blocks(tsdf_hash *h, const int32_t *keys, int64_t n, int64_t *removed)
 {
     BAD_ARG(!h || (!keys && n > 0), "NULL argument");

@@ -448,6 +448,34 @@ __global__ void k_count_voxels(HashDev h, unsigned long long *total)
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
 }
 
+// Read-out gather (world > 1): block lists exported by every rank (keys [n][3], payload [n][3][512] with colour in
+// the float encoding) are scattered into dense volumes that the caller pre-filled with the defaults.  One CTA per
+// block, same voxel order as k_scatter_dense.
+__global__ void k_scatter_block_list(const int32_t *__restrict__ keys, const float *__restrict__ payload, int n, int dim_x,
+                                     int dim_y, int dim_z, float *tsdf, float *wgt, float *col)
+{
+    const int t = threadIdx.x, lx = t >> 3, ly = t & 7;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int bx = keys[3 * b], by = keys[3 * b + 1], bz = keys[3 * b + 2];
+        const int gx = bx * BRICK + lx, gy = by * BRICK + ly;
+        if (gx >= dim_x || gy >= dim_y) continue;
+        const float *rec = payload + (size_t)b * BRICK_FLOATS + 8 * t;
+        const size_t base = ((size_t)gx * dim_y + gy) * dim_z + (size_t)bz * BRICK;
+        for (int k = 0; k < BRICK && bz * BRICK + k < dim_z; ++k) {
+            if (tsdf) tsdf[base + k] = rec[k];
+            if (wgt) wgt[base + k] = rec[BRICK_VOX + k];
+            if (col) col[base + k] = rec[2 * BRICK_VOX + k];
+        }
+    }
+}
+
+void launch_scatter_block_list(const int32_t *keys, const float *payload, int n, int dim_x, int dim_y, int dim_z, float *tsdf,
+                               float *wgt, float *col, bool fill, int sm_count, cudaStream_t s)
+{
+    if (fill) k_fill_dense<<<sm_count * 8, 256, 0, s>>>(tsdf, wgt, col, (size_t)dim_x * dim_y * dim_z);
+    if (n > 0) k_scatter_block_list<<<sm_count * 16, INTEGRATE_THREADS, 0, s>>>(keys, payload, n, dim_x, dim_y, dim_z, tsdf, wgt, col);
+}
+
 void launch_voxel_query(const HashDev &h, const int32_t *coords, int n, int mode, float *out, uint8_t *found, cudaStream_t s)
 {
     if (n <= 0) return;

@@ -140,6 +140,8 @@ void launch_scatter_dense(const HashDev &h, int dim_x, int dim_y, int dim_z, flo
                           int sm_count, cudaStream_t s);
 void launch_export_blocks(const HashDev &h, int capacity, int *count, int32_t *keys_out, float *payload, int sm_count,
                           cudaStream_t s);
+void launch_scatter_block_list(const int32_t *keys, const float *payload, int n, int dim_x, int dim_y, int dim_z, float *tsdf,
+                               float *wgt, float *col, bool fill, int sm_count, cudaStream_t s);
 void launch_voxel_query(const HashDev &h, const int32_t *coords, int n, int mode, float *out, uint8_t *found, cudaStream_t s);
 void launch_count_voxels(const HashDev &h, unsigned long long *total, int sm_count, cudaStream_t s);
 void launch_remove_blocks(const HashDev &h, const int32_t *keys, int n, int *removed, cudaStream_t s);

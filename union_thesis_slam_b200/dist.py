@@ -77,6 +77,32 @@ def gather_x_sheets(local, dim_x, rank, world, group=None):
     return full
 
 
+def gather_block_lists(keys, payload, group=None):
+    """Read-out gather of the hash map: every rank contributes its block list -- keys [n, 3] int32,
+    payload [n, 3*512] float32 -- and receives the concatenation over ranks.  Counts are exchanged first, the lists
+    are padded to the longest and all-gathered (two collectives of the blocks' own size instead of three all-reduces
+    of dense volumes), then compacted.  Works on whatever backend the group uses (NCCL tensors on the GPU, gloo in the
+    CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([keys.shape[0]], dtype=torch.int64, device=keys.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = [int(c) for c in counts.tolist()]
+    n_max = max(max(counts), 1)
+    k_pad = torch.zeros((n_max, 3), dtype=keys.dtype, device=keys.device)
+    p_pad = torch.zeros((n_max, payload.shape[1]), dtype=payload.dtype, device=payload.device)
+    k_pad[:keys.shape[0]] = keys
+    p_pad[:payload.shape[0]] = payload
+    k_all = torch.empty((world * n_max, 3), dtype=keys.dtype, device=keys.device)
+    p_all = torch.empty((world * n_max, payload.shape[1]), dtype=payload.dtype, device=payload.device)
+    dist.all_gather_into_tensor(k_all, k_pad, group=group)
+    dist.all_gather_into_tensor(p_all, p_pad, group=group)
+    sel = torch.cat([torch.arange(r * n_max, r * n_max + counts[r], device=keys.device) for r in range(world)])
+    return k_all[sel].contiguous(), p_all[sel].contiguous()
+
+
 def merge_disjoint_volumes(tsdf, weight, color, group=None):
     """Hash read-out: every rank scattered only its own blocks into dense volumes with the
     defaults (1, 0, 0) elsewhere.  Blocks are disjoint and a voxel that was never updated holds

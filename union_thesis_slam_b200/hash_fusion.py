@@ -132,12 +132,34 @@ class HashTable:
             return t, w, c
         import torch
         dev = torch.device("cuda", self.device)
-        t = torch.empty(shape, dtype=torch.float32, device=dev)
-        w = torch.empty(shape, dtype=torch.float32, device=dev)
-        c = torch.empty(shape, dtype=torch.float32, device=dev)
-        _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
-        t, w, c = dist.merge_disjoint_volumes(t, w, c, self._group)
+        t, w, c = self._gathered_device_volume(dev, want_weight=True)
         return t.cpu().numpy(), w.cpu().numpy(), c.cpu().numpy()
+
+    def export_blocks_device(self, dev):
+        """This rank's blocks as device tensors: keys [n,3] int32, payload [n, 3*512] float32."""
+        import torch
+        n = C.c_int64()
+        _capi.check(self._lib.vh_export_blocks_device(self._handle, 0, C.byref(n), None, None))
+        keys = torch.empty((max(n.value, 1), 3), dtype=torch.int32, device=dev)
+        payload = torch.empty((max(n.value, 1), 3 * BLOCK ** 3), dtype=torch.float32, device=dev)
+        if n.value:
+            _capi.check(self._lib.vh_export_blocks_device(self._handle, n.value, C.byref(n), _capi.ptr(keys),
+                                                          _capi.ptr(payload)))
+        return keys[:n.value], payload[:n.value]
+
+    def _gathered_device_volume(self, dev, want_weight=False):
+        """Read-out at world > 1: exchange BLOCK LISTS (dist.gather_block_lists) and scatter the union into dense device
+        volumes on every rank -- bit-exact by construction, blocks are disjoint across ranks."""
+        import torch
+        keys, payload = self.export_blocks_device(dev)
+        keys, payload = dist.gather_block_lists(keys, payload, self._group)
+        shape = tuple(int(d) for d in self._vol_dim)
+        t = torch.empty(shape, dtype=torch.float32, device=dev)
+        c = torch.empty(shape, dtype=torch.float32, device=dev)
+        w = torch.empty(shape, dtype=torch.float32, device=dev) if want_weight else None
+        _capi.check(self._lib.vh_scatter_blocks_device(self._handle, _capi.ptr(keys), _capi.ptr(payload), keys.shape[0], 1,
+                                                       _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
+        return t, w, c
 
     def get_volume(self):
         """tsdf (default 1) and colour (default 0) volumes (reference hash_fusion.py:442-463)."""
@@ -326,9 +348,7 @@ class HashTable:
         if self.world_size == 1:
             _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), None, _capi.ptr(c)))
             return t, c
-        w = torch.empty(shape, dtype=torch.float32, device=dev)
-        _capi.check(self._lib.vh_to_dense_device(self._handle, _capi.ptr(t), _capi.ptr(w), _capi.ptr(c)))
-        t, w, c = dist.merge_disjoint_volumes(t, w, c, self._group)
+        t, _, c = self._gathered_device_volume(dev)
         return t, c
 
     def get_mesh(self):
