@@ -290,3 +290,30 @@ def test_per_voxel_mode_matches_oracles_on_random_case():
     assert np.array_equal(vox[:, 1], oh.color[idx])
     assert ht.voxel_table.stats()["resizes"] == ot.resizes >= 1
     ht.close()
+
+
+def test_returned_entries_write_through_or_refuse():
+    """Reference hash_fusion.py:145: `target_entry.integrate_voxel(...)` mutates the stored voxel.  Entries of the
+    device container write through; snapshots of voxels in the block map refuse mutation instead of dropping it."""
+    import scenes
+    from union_thesis_slam_b200 import bucket_table, hash_fusion
+    vt = bucket_table.VoxelBucketTable(64)
+    orc = bo.OracleBucketTable(64)
+    c1, c2 = float(7 * 65536 + 8 * 256 + 9), float(100 * 65536 + 50 * 256 + 25)
+    vt.integrate_voxels([[3, 4, 5]], [0.25], [c1])
+    orc.integrate([3, 4, 5], 0.25, c1)
+    e = vt.get_hash_entry([3, 4, 5])
+    e.integrate_voxel(-0.5, c2)
+    b, s_ = orc.integrate([3, 4, 5], -0.5, c2)
+    want = orc.vox[orc._i(b, s_)]
+    got = vt.get_hash_entry([3, 4, 5]).get_voxel()
+    assert (got.get_sdf(), got.get_color(), got.get_weight()) == tuple(want)
+    assert (e.get_voxel().get_sdf(), e.get_voxel().get_weight()) == (want[0], want[2])   # the handed-out object follows
+    case = scenes.small_case(7, dims=(24, 24, 24), voxel_size=0.02, nframes=1)
+    ht = hash_fusion.HashTable(case["vol_bnds"].copy(), 0.02, map_size=4096)
+    c, d, p, _ = case["frames"][0]
+    ht.integrate(c, d, case["K"], p)
+    _, w, _ = ht.get_volume_with_weight()
+    v = np.argwhere(w > 0)[0]
+    with pytest.raises(TypeError):
+        ht.get_voxel(v).integrate(0.1, 0.0)

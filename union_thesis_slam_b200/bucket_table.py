@@ -75,6 +75,39 @@ class HashEntry:
         return np.array_equal(self._position, position)
 
 
+class _LiveVoxel(Voxel):
+    """Voxel of an entry returned by ``VoxelBucketTable.get_hash_entry``: ``integrate`` writes through to the
+    device table (the reference returns the live object, hash_fusion.py:145), then refreshes this snapshot."""
+
+    def __init__(self, table, position, sdf, color, weight):
+        super().__init__(sdf, color, weight)
+        self._table, self._position = table, position
+
+    def integrate(self, new_dist, new_color, obs_weight=1.):
+        if obs_weight != 1.:
+            raise ValueError("the device container integrates with obs_weight 1, like the reference's own loop "
+                             "(hash_fusion.py:141,145)")
+        self._table.integrate_voxels([self._position], [new_dist], [new_color])
+        _, vox = self._table.lookup([self._position], with_voxels=True)
+        self._sdf, self._color, self._weight = float(vox[0, 0]), float(vox[0, 1]), float(vox[0, 2])
+
+
+class _LiveHashEntry(HashEntry):
+    def integrate_voxel(self, new_dist, new_color, obs_weight=1.):
+        """hash_entry.py:18-21, executed on the device table."""
+        self._voxel.integrate(new_dist, new_color, obs_weight)
+
+
+class FrozenVoxel(Voxel):
+    """Snapshot of a voxel that ``HashTable.integrate`` wrote into the block map: read-only.  The reference hands
+    out the live object; here the map lives on the device, so mutation has to go through ``HashTable.integrate`` or
+    ``HashTable.remove`` -- calling ``integrate`` on the snapshot raises instead of silently changing nothing."""
+
+    def integrate(self, new_dist, new_color, obs_weight=1.):
+        raise TypeError("read-only snapshot of a voxel of the device block map: update the map with "
+                        "HashTable.integrate(); HashTable.remove(coord) deletes the entry")
+
+
 class Bucket:
     """Host-side value type of data_structures/bucket.py:7-143: a fixed list of ``bucket_size``
     entry slots, the last one reserved for the head of the bucket's collision chain.  The device
@@ -257,13 +290,15 @@ class VoxelBucketTable:
         return self.apply(np.full(len(pos), OP_ADD, np.int32), pos, args)
 
     def get_hash_entry(self, world_coord):
-        """Snapshot of the stored entry or None (hash_fusion.py:285-310)."""
+        """The stored entry or None (hash_fusion.py:285-310): a snapshot whose ``integrate_voxel`` /
+        ``get_voxel().integrate`` write through to the device table."""
         slots, vox = self.lookup([world_coord], with_voxels=True)
         b, e = int(slots[0, 0]), int(slots[0, 1])
         if b < 0:
             return None
-        voxel = None if math.isnan(vox[0, 0]) else Voxel(vox[0, 0], vox[0, 1], vox[0, 2])
-        entry = HashEntry(tuple(int(v) for v in world_coord[:3]), None, voxel)
+        pos = tuple(int(v) for v in world_coord[:3])
+        voxel = None if math.isnan(vox[0, 0]) else _LiveVoxel(self, pos, vox[0, 0], vox[0, 1], vox[0, 2])
+        entry = _LiveHashEntry(pos, None, voxel)
         entry.slot = (b, e)
         return entry
 

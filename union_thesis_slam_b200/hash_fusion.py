@@ -234,7 +234,7 @@ class HashTable:
             return None
         from . import bucket_table
         pos = [int(v) for v in np.asarray(world_coord).reshape(-1)[:3]]
-        return bucket_table.HashEntry(pos, None, bucket_table.Voxel(float(out[0, 0]), float(out[0, 2]), float(out[0, 1])))
+        return bucket_table.HashEntry(pos, None, bucket_table.FrozenVoxel(float(out[0, 0]), float(out[0, 2]), float(out[0, 1])))
 
     def get_voxel(self, world_coord):
         """The voxel of a coordinate, or None when it has no entry (the reference raises AttributeError
