@@ -237,16 +237,21 @@ __global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickR
 }
 
 // K5: per-block integration.
+#ifndef INTEGRATE_HASH_MIN_CTAS
+#define INTEGRATE_HASH_MIN_CTAS INTEGRATE_MIN_CTAS
+#endif
 template <bool UNIT_W>
-__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_MIN_CTAS)
+__global__ void __launch_bounds__(INTEGRATE_THREADS, INTEGRATE_HASH_MIN_CTAS)
 k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__restrict__ list, FrameScratch *fs, Totals *tot,
                  UpdateCounters uc)
 {
     __shared__ uint32_t s_storage;
+    // per-thread update counter in shared memory (a fire-and-forget add per column instead of a spilled register)
+    __shared__ unsigned s_updates[INTEGRATE_THREADS];
     const int n = fs->vis_count;
     const int t = threadIdx.x;
     const int lx = t >> 3, ly = t & 7;
-    unsigned my_updates = 0;
+    s_updates[t] = 0;
     int b = blockIdx.x;
     int4 br_next = make_int4(0, 0, 0, 0);
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
@@ -288,10 +293,13 @@ k_integrate_hash(FrameParams f, VolumeParams v, HashDev h, const BrickRef *__res
             __stcs(reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX), zero);
             __stcs(reinterpret_cast<float4 *>(rec + 2 * BRICK_VOX) + 1, zero);
         }
-        if (inb)
-            my_updates += integrate_column8<UNIT_W, false>(f, v, gx, gy, gz0,
-                                                           h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t);
+        if (inb) {
+            const unsigned nupd = integrate_column8<UNIT_W, false>(f, v, gx, gy, gz0,
+                                                                    h.blocks + (size_t)storage * BRICK_FLOATS + 8 * t);
+            if (nupd) atomicAdd(&s_updates[t], nupd);
+        }
     }
+    unsigned my_updates = s_updates[t];
     for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
     if ((t & 31) == 0) { // one private slot per warp: no atomics
         const int w = blockIdx.x * (INTEGRATE_THREADS / 32) + (t >> 5);
