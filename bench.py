@@ -98,6 +98,17 @@ class ClockSampler:
                 pass
             time.sleep(0.001)
 
+    def sample_now(self):
+        """One sample taken by the calling thread (the timed region is shorter than a thread switch interval:
+        the benchmark calls this while the device is still busy with the steps it has just been issued)."""
+        if self.fallback is None:
+            try:
+                nv = self.nv
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                pass
+
     def mark(self):
         self.t0 = time.perf_counter()
 
@@ -125,7 +136,8 @@ class ClockSampler:
         return {"sm_mhz": sm_t if timed else sm_all, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(set(reasons_t) | set(reasons_all)), "samples": len(timed),
                 "samples_measured_section": len(self.samples), "sm_mhz_measured_section": sm_all,
-                "source": "NVML polling thread (1 ms); `samples` lie inside the timed region"}
+                "source": "NVML: polling thread (1 ms) + samples taken by the main thread while the timed steps "
+                          "execute; `samples` lie inside the timed region"}
 
 
 class _SmiSampler:
@@ -358,7 +370,7 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def timed_device(D, vol, step, n, first):
+def timed_device(D, vol, step, n, first, sampler=None):
     """Device time of n frames: CUDA events on the handle's own stream bracketed by barrier + synchronize,
     max over ranks.  Returns (ms, updates summed over ranks)."""
     torch = D.torch
@@ -371,6 +383,9 @@ def timed_device(D, vol, step, n, first):
         step(first + i)
     vol.flush()  # integrate kernels run on sibling streams: join them (on the device) before the end event
     e1.record(stream)
+    if sampler:
+        for _ in range(3):   # the host is ahead of the device here: these samples see the timed steps executing
+            sampler.sample_now()
     vol.sync()
     D.barrier()
     ms = D.max(e0.elapsed_time(e1))
@@ -424,7 +439,7 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.mark()
-    ms, upd = timed_device(D, vol, step, args.steps, args.warmup)
+    ms, upd = timed_device(D, vol, step, args.steps, args.warmup, sampler)
     if sampler:
         sampler.unmark()
     value = upd / (ms * 1e-3)
@@ -783,6 +798,7 @@ def main():
 def _main(out):
     global _OUT
     _OUT = out
+    sys.setswitchinterval(0.0005)  # let the clock-sampling thread run inside millisecond-long timed regions
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1024)
