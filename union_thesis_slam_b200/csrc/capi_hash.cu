@@ -223,15 +223,16 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     CUDA_TRY(cudaGetLastError());
     const double n_sb = (double)h->dev.nsx * h->dev.nsy * h->dev.nsz;
     const bool ray_walk = h->alloc_mode == 1 || (h->alloc_mode == 2 && n_sb > WALK_SB_PER_TILE * tiles_x * tiles_y);
+    // the frame's visible-super-block bitmap: written by the walk or by the scan, read by refine and compaction
+    CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
     if (ray_walk) {
-        CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
         launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
         CUDA_TRY(cudaGetLastError());
     }
-    launch_refine_insert(f, c, h->dev, ray_walk ? h->sb_flags : nullptr, h->io.fs, h->tot, s);
+    launch_refine_insert(f, c, h->dev, h->sb_flags, ray_walk, h->io.fs, h->tot, s);
     CUDA_TRY(cudaGetLastError());
     // a key exists at most once per block of the bounded grid: bound the scan by that, not by the table size
-    launch_compact_visible(f, c, h->dev, (int)std::min<int64_t>(h->table_slots, (int64_t)h->dev.nbx * h->dev.nby * h->dev.nbz),
+    launch_compact_visible(f, c, h->dev, h->sb_flags, (int)std::min<int64_t>(h->table_slots, (int64_t)h->dev.nbx * h->dev.nby * h->dev.nbz),
                            list, h->io.fs, s);
     CUDA_TRY(cudaGetLastError());
     if ((rc = h->io.prepared())) return rc;

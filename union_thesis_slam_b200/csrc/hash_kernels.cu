@@ -180,19 +180,23 @@ __global__ void k_walk_coarse(WalkParams w, HashDev h, const float *__restrict__
 // frustum + tile-depth-pyramid test of the bounded super-block grid) and K2 is not run at all.  A block whose key
 // is already in the table (presence bitmap) costs one bit test; otherwise the conservative
 // visibility test of the dense grid decides and the key is inserted lock-free (keys only).
-__global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, const uint32_t *__restrict__ sb_flags,
+__global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, uint32_t *__restrict__ sb_flags, int walked,
                                 FrameScratch *fs, Totals *tot)
 {
     const int sb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (sb >= h.nsx * h.nsy * h.nsz) return;
-    if (sb_flags && !((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
+    if (walked && !((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
     const int sz = sb % h.nsz, sy = (sb / h.nsz) % h.nsy, sx = sb / (h.nsz * h.nsy);
     c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
     if (!(c.max_depth > 0.0)) return;
     // grid-scan allocation (no ray walk ran): the conservative visibility test of the whole
     // super-block stands in for the walk's flag (warp-uniform)
-    if (!sb_flags && !superblock_visible(f, c, sx, sy, sz)) return;
+    if (!walked) {
+        if (!superblock_visible(f, c, sx, sy, sz)) return;
+        // the frame's visible-super-block bitmap also gates the compaction pass (k_compact_visible)
+        if (lane == 0) atomicOr(sb_flags + (sb >> 5), 1u << (sb & 31));
+    }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int child = lane * 2 + k;
@@ -200,15 +204,19 @@ __global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, const ui
         if (bx >= h.nbx || by >= h.nby || bz >= h.nbz) continue;
         const uint32_t bit = (uint32_t)((bx * h.nby + by) * h.nbz + bz);
         if ((h.known[bit >> 5] >> (bit & 31u)) & 1u) continue;
-        if (!brick_visible(f, c, bx, by, bz)) continue;
         const unsigned long long key = pack_key(bx, by, bz);
-        if (h.world == 1 || owner_of(key, h.world) == h.rank) table_insert(h, key, bx, by, bz, fs, tot);
+        const bool ours = h.world == 1 || owner_of(key, h.world) == h.rank;
+        if (ours) { // the owner decides first: another rank's block costs no visibility test at all
+            if (!brick_visible(f, c, bx, by, bz)) continue;
+            table_insert(h, key, bx, by, bz, fs, tot);
+        }
         atomicOr(h.known + (bit >> 5), 1u << (bit & 31u)); // ours and inserted, or not ours: never test again
     }
 }
 
 // K4: visible-block compaction over the entry list.
-__global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickRef *__restrict__ list, FrameScratch *fs)
+__global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, const uint32_t *__restrict__ sb_flags,
+                                  BrickRef *__restrict__ list, FrameScratch *fs)
 {
     const int n = *h.n_entries;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,7 +228,9 @@ __global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, BrickR
         slot = h.entries[i];
         unpack_key(h.keys[slot], bx, by, bz);
         c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
-        vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
+        // entries of super-blocks the frame cannot touch (bitmap written by the allocation pass) cost one bit test
+        const int sb = ((bx >> 2) * h.nsy + (by >> 2)) * h.nsz + (bz >> 2);
+        vis = c.max_depth > 0.0 && ((sb_flags[sb >> 5] >> (sb & 31)) & 1u) && brick_visible(f, c, bx, by, bz);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, vis);
     if (!ballot) return;
@@ -505,18 +515,18 @@ void launch_walk_coarse(const WalkParams &w, const HashDev &h, const float *tile
     k_walk_coarse<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(w, h, tile_dmax, sb_flags, fs);
 }
 
-void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, uint32_t *sb_flags, bool walked,
                           FrameScratch *fs, Totals *tot, cudaStream_t s)
 {
     const long long warps = (long long)h.nsx * h.nsy * h.nsz;
-    k_refine_insert<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(f, c, h, sb_flags, fs, tot);
+    k_refine_insert<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(f, c, h, sb_flags, walked ? 1 : 0, fs, tot);
 }
 
-void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
-                            BrickRef *list, FrameScratch *fs, cudaStream_t s)
+void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+                            int max_entries, BrickRef *list, FrameScratch *fs, cudaStream_t s)
 {
     if (max_entries <= 0) return;
-    k_compact_visible<<<(max_entries + 127) / 128, 128, 0, s>>>(f, c, h, list, fs);
+    k_compact_visible<<<(max_entries + 127) / 128, 128, 0, s>>>(f, c, h, sb_flags, list, fs);
 }
 
 int integrate_hash_ctas_per_sm()

@@ -129,10 +129,10 @@ struct WalkParams {
 void launch_hash_init(const HashDev &h, int sm_count, cudaStream_t s);
 void launch_walk_coarse(const WalkParams &w, const HashDev &h, const float *tile_dmax, uint32_t *sb_flags,
                         FrameScratch *fs, cudaStream_t s);
-void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+void launch_refine_insert(const FrameParams &f, const CullParams &c, const HashDev &h, uint32_t *sb_flags, bool walked,
                           FrameScratch *fs, Totals *tot, cudaStream_t s);
-void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, int max_entries,
-                            BrickRef *list, FrameScratch *fs, cudaStream_t s);
+void launch_compact_visible(const FrameParams &f, const CullParams &c, const HashDev &h, const uint32_t *sb_flags,
+                            int max_entries, BrickRef *list, FrameScratch *fs, cudaStream_t s);
 int integrate_hash_ctas_per_sm();
 void launch_integrate_hash(const FrameParams &f, const VolumeParams &v, const HashDev &h, const BrickRef *list,
                            FrameScratch *fs, Totals *tot, UpdateCounters uc, int grid, cudaStream_t s);
