@@ -210,8 +210,10 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     if (!PROBE) {
 #if RECORD_LOAD_EARLY
         // volatile: the compiler otherwise sinks these loads below the depth-test branch, which puts the
-        // record's DRAM latency AFTER the pixels' instead of beside it
-        T4 = ldcs_early(rec);
+        // record's DRAM latency AFTER the pixels' instead of beside it.  Mode 2 issues only the weight and
+        // colour planes early (8 registers instead of 12) and leaves the tsdf plane where ptxas puts it.
+        if (RECORD_LOAD_EARLY == 1) T4 = ldcs_early(rec);
+        else T4 = __ldcs(reinterpret_cast<const float4 *>(rec));
         W4 = ldcs_early(rec + BRICK_VOX);
         const float4 c4 = ldcs_early(rec + 2 * BRICK_VOX);
         C4 = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
