@@ -593,11 +593,12 @@ def cpu_baselines(frames, K, room):
 
 
 def fixture_frames():
-    """The 12 frames of the bundled sequence kept under tests/golden/frames, decoded as grid_demo1.py:80-84."""
+    """The first 100 frames of the bundled sequence kept under tests/golden/frames (in order, as the reference's demo
+    integrates them), decoded as grid_demo1.py:80-84."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import frames as fx
     import scenes
-    idx = list(range(10)) + [500, 999]
+    idx = [i for i in range(100) if os.path.exists(os.path.join(fx.FRAMES_DIR, "frame-%06d.depth.png" % i))]
     return [fx.load_frame(i, check=False) for i in idx], fx.intrinsics(), np.array(scenes.CONFIG1_BOUNDS)
 
 
@@ -638,11 +639,11 @@ def bench_configs(args, D):
     if D.world == 1:
         frs, Kf, bounds = fixture_frames()
         for batch in (1, 4):
-            run("config0_2cm_batch%d" % batch, bounds, 0.02, frs, Kf, batch, 8,
-                "BASELINE.json configs[0]: 12 frames of the bundled 640x480 sequence (tests/golden/frames) cycled, "
-                "dense grid at 2 cm over the sequence's bounds")
-        run("config2_5mm", bounds, 0.005, frs, Kf, 1, 2,
-            "BASELINE.json configs[2]: the bundled frames cycled into a 5 mm grid over the same bounds (23.6 GB)")
+            run("config0_2cm_batch%d" % batch, bounds, 0.02, frs, Kf, batch, 2,
+                "BASELINE.json configs[0]: the first %d frames of the bundled 640x480 sequence (tests/golden/frames) in "
+                "order, replayed, dense grid at 2 cm over the sequence's bounds" % len(frs))
+        run("config2_5mm", bounds, 0.005, frs, Kf, 1, 1,
+            "BASELINE.json configs[2]: the same frames replayed into a 5 mm grid over the same bounds (23.6 GB)")
     room = synth.room_bounds(ROOM)
     frs, Kr = synth.room_stream(8, room, seed=0)
     run("config3_48GB_reading", room, 0.00464, frs, Kr, 1, 1,

@@ -100,3 +100,42 @@ def test_bench_room_steady_state_oracle_sheets():
         assert np.array_equal(got, want[which]), "plane %d differs on the oracle sheets (%d voxels)" % (
             which, int((got != want[which]).sum()))
     vol.close()
+
+
+def test_config1_first_100_frames_sha256_equals_reference():
+    """The first 100 frames of the bundled sequence in order at 2 cm: sha256 of all three planes equals the UNMODIFIED
+    reference after 50 and 100 frames (tests/golden/golden_long.json == SURVEY Appendix B rows 50 and 100; weights to 100,
+    real sensor data)."""
+    from union_thesis_slam_b200 import grid_fusion
+    G = frames.golden_long()
+    K = frames.intrinsics()
+    vol = grid_fusion.TSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    for n, i in enumerate(range(100), 1):
+        c, d, p = frames.load_frame(i)
+        vol.integrate(c, d, K, p, obs_weight=1.)
+        if str(n) in G["dense"]:
+            g = G["dense"][str(n)]
+            t, w, col = _state(vol)
+            assert (frames.sha(w), frames.sha(t), frames.sha(col)) == (g["weight"], g["tsdf"], g["color"]), "after %d frames" % n
+            assert int((w > 0).sum()) == g["n_w_pos"] and float(w.max()) == g["max_w"]
+            assert vol.stats()["updated_total"] == g["sum_w"]
+
+
+def test_config1_first_100_frames_hash_and_batched_dense_equal_reference():
+    """Same 100 frames into the hash map and into a dense grid with 4 frames per brick visit: both reproduce the
+    reference's planes (the hash map through get_volume: hash == dense bit for bit)."""
+    from union_thesis_slam_b200 import grid_fusion, hash_fusion
+    g = frames.golden_long()["dense"]["100"]
+    K = frames.intrinsics()
+    vol = grid_fusion.TSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    vol.set_batch(4)
+    ht = hash_fusion.HashTable(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL, map_size=1 << 16)
+    for i in range(100):
+        c, d, p = frames.load_frame(i, check=False)
+        vol.integrate(c, d, K, p, obs_weight=1.)
+        ht.integrate(c, d, K, p, obs_weight=1.)
+    t, w, col = _state(vol)
+    assert (frames.sha(w), frames.sha(t), frames.sha(col)) == (g["weight"], g["tsdf"], g["color"])
+    ht_t, ht_w, ht_c = ht.get_volume_with_weight()
+    assert (frames.sha(ht_w), frames.sha(ht_t), frames.sha(ht_c)) == (g["weight"], g["tsdf"], g["color"])
+    assert ht.count_num_hash_entries() == g["n_w_pos"]

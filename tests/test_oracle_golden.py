@@ -138,3 +138,19 @@ def test_slab_and_cyclic_shards_union_equals_single():
                 vol.integrate(c, d, z["K"], p, obs_weight=obs)
             t[xs], w[xs], col[xs] = vol._tsdf_vol_cpu, vol._weight_vol_cpu, vol._color_vol_cpu
         assert np.array_equal(t, z["tsdf"]) and np.array_equal(w, z["weight"]) and np.array_equal(col, z["color_vol"])
+
+
+def test_oracle_first_100_frames_equal_reference_and_survey_appendix_b():
+    """C oracle over the first 100 bundled frames against the reference's digests (golden_long.json), which the
+    generating script also checked against SURVEY.md Appendix B (rows 50 and 100)."""
+    G = frames.golden_long()
+    K = frames.intrinsics()
+    orc = oracle.OracleTSDFVolume(np.array(scenes.CONFIG1_BOUNDS), scenes.CONFIG1_VOXEL)
+    for n, i in enumerate(range(100), 1):
+        c, d, p = frames.load_frame(i)
+        orc.integrate(c, d, K, p, obs_weight=1.)
+        if str(n) in G["dense"]:
+            g = G["dense"][str(n)]
+            assert (frames.sha(orc._weight_vol_cpu), frames.sha(orc._tsdf_vol_cpu), frames.sha(orc._color_vol_cpu)) == (
+                g["weight"], g["tsdf"], g["color"]), "after %d frames" % n
+    assert G["dense"]["50"]["tsdf"].startswith("2e9bb509beb8d38d") and G["dense"]["100"]["color"].startswith("fe43593d4f315064")
