@@ -130,6 +130,7 @@ int make_frame_params(FrameParams *f, CullParams *c, const VolumeGeom &g, int H,
     for (int r = 0; r < 3; ++r)
         c->Tn[r] = sqrt(Tinv[4 * r] * Tinv[4 * r] + Tinv[4 * r + 1] * Tinv[4 * r + 1] + Tinv[4 * r + 2] * Tinv[4 * r + 2]) * 1.0000001;
     c->max_depth = 0.0;
+    c->tag = 0; // set by the handle when the frame is prepared
     c->rho = g.brick_radius();
     c->vs = g.vs;
     c->ox = (double)g.origin[0];
@@ -228,12 +229,6 @@ int FrameIO::set_subs(int n)
     return TSDF_OK;
 }
 
-int FrameIO::clear_sub(int sub)
-{
-    CUDA_TRY(cudaMemsetAsync(scratch_slot[prep_index(slot, sub)], 0, clear_bytes, pre));
-    return TSDF_OK;
-}
-
 int FrameIO::release_upload_after_prep()
 {
     if (cur >= 0) {
@@ -255,9 +250,8 @@ int FrameIO::ensure_tiles(int H, int W)
         p.tx[l] = (W + (8 << l) - 1) / (8 << l);
         p.ty[l] = (H + (8 << l) - 1) / (8 << l);
         off[l] = total;
-        total += (((size_t)p.tx[l] * p.ty[l] * sizeof(float)) + 255) / 256 * 256;
+        total += (((size_t)p.tx[l] * p.ty[l] * sizeof(unsigned long long)) + 255) / 256 * 256; // tagged 64-bit maxima
     }
-    clear_bytes = total;
     p.tx[0] = (W + 7) / 8;
     p.ty[0] = (H + 7) / 8;
     off[0] = total;
@@ -268,9 +262,10 @@ int FrameIO::ensure_tiles(int H, int W)
     }
     for (int i = 0; i < FRAME_SLOTS * subs; ++i) {
         CUDA_TRY(cudaMalloc(&scratch_slot[i], total));
-        CUDA_TRY(cudaMemset(scratch_slot[i], 0, total));
+        CUDA_TRY(cudaMemset(scratch_slot[i], 0, total)); // once: tag 0 is never used, so everything reads as "no depth"
         pyr_slot[i] = p;
-        for (int l = 0; l < 4; ++l) pyr_slot[i].level[l] = reinterpret_cast<float *>(scratch_slot[i] + off[l]);
+        pyr_slot[i].level0 = reinterpret_cast<float *>(scratch_slot[i] + off[0]);
+        for (int l = 1; l < 4; ++l) pyr_slot[i].up[l - 1] = reinterpret_cast<unsigned long long *>(scratch_slot[i] + off[l]);
     }
     fs = nullptr;
     tiles_H = H;
@@ -374,8 +369,7 @@ int FrameIO::begin_kernels()
     for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_int_done[k][slot], 0));
     if (stat_used) CUDA_TRY(cudaStreamWaitEvent(pre, stat_done[slot], 0)); // a counter snapshot may still read the slot
     if (timing) CUDA_TRY(cudaEventRecord(k_begin, pre));
-    CUDA_TRY(cudaMemsetAsync(scratch_slot[slot], 0, clear_bytes, pre));
-    n_marks = 0;
+    n_marks = 0; // no memset: k_prep_frame zeroes the slot's counters, the maxima are tagged per frame
     return TSDF_OK;
 }
 
@@ -770,10 +764,7 @@ static int grid_enqueue(tsdf_grid *g, const uint8_t *d_rgb, const double *d_dept
     if (g->q_n && (g->q_f[0].H != H || g->q_f[0].W != W) && (rc = grid_flush_batch(g))) return rc;
     if ((rc = g->io.ensure_px(H * W)) || (rc = g->io.ensure_tiles(H, W))) return rc;
     const int sub = g->q_n;
-    if (sub == 0) {
-        if ((rc = g->io.begin_kernels())) return rc; // picks the slot, waits for its previous user, clears sub 0
-    } else if ((rc = g->io.clear_sub(sub)))
-        return rc;
+    if (sub == 0 && (rc = g->io.begin_kernels())) return rc; // picks the slot, waits for its previous user
     const int pi = FrameIO::prep_index(g->io.slot, sub);
     FrameScratch *fs = reinterpret_cast<FrameScratch *>(g->io.scratch_slot[pi]);
     c.pyr = g->io.pyr_slot[pi];
@@ -781,7 +772,8 @@ static int grid_enqueue(tsdf_grid *g, const uint8_t *d_rgb, const double *d_dept
     f.px = g->io.px_slot[pi];
     g->unit_w = g->unit_w && f.obs == 1.0;
     f.unit_w = g->unit_w ? 1 : 0;
-    launch_prep_frame(d_rgb, d_depth, g->io.px_slot[pi], fs, g->io.pyr_slot[pi], H, W, g->io.pre);
+    c.tag = g->io.next_tag();
+    launch_prep_frame(d_rgb, d_depth, g->io.px_slot[pi], fs, g->io.pyr_slot[pi], H, W, c.tag, g->io.pre);
     CUDA_TRY(cudaGetLastError());
     if ((rc = g->io.release_upload_after_prep())) return rc;
     g->q_f[sub] = f;

@@ -219,14 +219,15 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     // allocation + compaction (stream `pre`; they only insert keys and read table state, so they
     // overlap the previous frame's integrate kernel, which only touches records / vals / the heap)
     cudaStream_t s = h->io.pre;
-    launch_prep_frame(d_rgb, d_depth, h->io.d_px, h->io.fs, h->io.pyr, H, W, s);
+    c.tag = h->io.next_tag();
+    launch_prep_frame(d_rgb, d_depth, h->io.d_px, h->io.fs, h->io.pyr, H, W, c.tag, s);
     CUDA_TRY(cudaGetLastError());
     const double n_sb = (double)h->dev.nsx * h->dev.nsy * h->dev.nsz;
     const bool ray_walk = h->alloc_mode == 1 || (h->alloc_mode == 2 && n_sb > WALK_SB_PER_TILE * tiles_x * tiles_y);
     // the frame's visible-super-block bitmap: written by the walk or by the scan, read by refine and compaction
     CUDA_TRY(cudaMemsetAsync(h->sb_flags, 0, h->sb_words * sizeof(uint32_t), s));
     if (ray_walk) {
-        launch_walk_coarse(w, h->dev, h->io.pyr.level[0], h->sb_flags, h->io.fs, s);
+        launch_walk_coarse(w, h->dev, h->io.pyr.level0, h->sb_flags, h->io.fs, s);
         CUDA_TRY(cudaGetLastError());
     }
     launch_refine_insert(f, c, h->dev, h->sb_flags, ray_walk, h->io.fs, h->tot, s);

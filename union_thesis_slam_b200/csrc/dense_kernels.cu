@@ -29,13 +29,18 @@ __global__ void k_fill_bricks(float4 *bricks, size_t n_float4)
 // grid_fusion.py:228-232 colour fold (as an exact integer), max valid depth of the frame and the
 // per-tile max-depth pyramid.  One warp per 8x8-pixel tile, two horizontally adjacent pixels per lane.
 __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__restrict__ depth,
-                             FramePixel *__restrict__ px, FrameScratch *fs, TilePyramid pyr, int H, int W)
+                             FramePixel *__restrict__ px, FrameScratch *fs, TilePyramid pyr, int H, int W, unsigned tag)
 {
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tile >= pyr.tx[0] * pyr.ty[0]) return;
-    if (tile == 0 && lane == 0) // sentinel pixel behind the image: what a voxel that projects nowhere reads
+    if (tile == 0 && lane == 0) {
+        // sentinel pixel behind the image: what a voxel that projects nowhere reads
         *reinterpret_cast<uint4 *>(px + (size_t)H * W) = make_uint4(0u, 0xFFF00000u, 0u, 0u);
+        // the frame's counters start at zero (nothing in this kernel uses them; the maxima are tagged instead)
+        fs->vis_count = 0; fs->updated = 0ull; fs->cand_count = 0; fs->new_keys = 0; fs->error = 0;
+        fs->vis_extra[0] = fs->vis_extra[1] = fs->vis_extra[2] = 0;
+    }
     const int tx = tile % pyr.tx[0], ty = tile / pyr.tx[0];
     const int v = ty * 8 + (lane >> 2), u = tx * 8 + (lane & 3) * 2;
     float m = 0.0f;
@@ -56,13 +61,13 @@ __global__ void k_prep_frame(const uint8_t *__restrict__ rgb, const double *__re
     }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
-        pyr.level[0][tile] = m;
+        pyr.level0[tile] = m;
         if (m > 0.0f) {
-            const unsigned bits = __float_as_uint(m);
-            atomicMax(reinterpret_cast<unsigned *>(pyr.level[1]) + (ty >> 1) * pyr.tx[1] + (tx >> 1), bits);
-            atomicMax(reinterpret_cast<unsigned *>(pyr.level[2]) + (ty >> 2) * pyr.tx[2] + (tx >> 2), bits);
-            atomicMax(reinterpret_cast<unsigned *>(pyr.level[3]) + (ty >> 3) * pyr.tx[3] + (tx >> 3), bits);
-            atomicMax(&fs->max_depth_bits, bits);
+            const unsigned long long v = ((unsigned long long)tag << 32) | __float_as_uint(m);
+            atomicMax(pyr.up[0] + (ty >> 1) * pyr.tx[1] + (tx >> 1), v);
+            atomicMax(pyr.up[1] + (ty >> 2) * pyr.tx[2] + (tx >> 2), v);
+            atomicMax(pyr.up[2] + (ty >> 3) * pyr.tx[3] + (tx >> 3), v);
+            atomicMax(&fs->max_depth_tagged, v);
         }
     }
 }
@@ -99,7 +104,7 @@ __global__ void k_cull_bricks(FrameParams f, CullParams c, int nlbx, int nby, in
         const int lbx = i / (nbz * nby);
         bx = sheet_of(lbx, rank, world);
         cls = (lbx + by + bz) % classes;
-        c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+        c.max_depth = (double)frame_max_depth(fs, c.tag);
         vis = c.max_depth > 0.0 && brick_visible(f, c, bx, by, bz);
     }
     if (!__ballot_sync(0xffffffffu, vis)) return;
@@ -144,7 +149,7 @@ __global__ void k_cull_bricks_batch(CullBatch cb, int nlbx, int nby, int nbz, in
 #pragma unroll 1
         for (int k = 0; k < cb.n; ++k) {
             CullParams c = cb.c[k];
-            c.max_depth = (double)__uint_as_float(cb.fs[k]->max_depth_bits);
+            c.max_depth = (double)frame_max_depth(cb.fs[k], c.tag);
             if (c.max_depth > 0.0 && brick_visible(cb.f[k], c, bx, by, bz)) mask |= 1u << k;
         }
     }
@@ -401,10 +406,10 @@ void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_
 }
 
 void launch_prep_frame(const uint8_t *rgb, const double *depth, FramePixel *px, FrameScratch *fs,
-                       const TilePyramid &pyr, int H, int W, cudaStream_t s)
+                       const TilePyramid &pyr, int H, int W, unsigned tag, cudaStream_t s)
 {
     const int warps = pyr.tx[0] * pyr.ty[0];
-    k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, px, fs, pyr, H, W);
+    k_prep_frame<<<(warps * 32 + 127) / 128, 128, 0, s>>>(rgb, depth, px, fs, pyr, H, W, tag);
 }
 
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s)

@@ -188,7 +188,7 @@ __global__ void k_refine_insert(FrameParams f, CullParams c, HashDev h, uint32_t
     if (sb >= h.nsx * h.nsy * h.nsz) return;
     if (walked && !((sb_flags[sb >> 5] >> (sb & 31)) & 1u)) return;
     const int sz = sb % h.nsz, sy = (sb / h.nsz) % h.nsy, sx = sb / (h.nsz * h.nsy);
-    c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+    c.max_depth = (double)frame_max_depth(fs, c.tag);
     if (!(c.max_depth > 0.0)) return;
     // grid-scan allocation (no ray walk ran): the conservative visibility test of the whole
     // super-block stands in for the walk's flag (warp-uniform)
@@ -227,7 +227,7 @@ __global__ void k_compact_visible(FrameParams f, CullParams c, HashDev h, const 
     if (i < n) {
         slot = h.entries[i];
         unpack_key(h.keys[slot], bx, by, bz);
-        c.max_depth = (double)__uint_as_float(fs->max_depth_bits);
+        c.max_depth = (double)frame_max_depth(fs, c.tag);
         // entries of super-blocks the frame cannot touch (bitmap written by the allocation pass) cost one bit test
         const int sb = ((bx >> 2) * h.nsy + (by >> 2)) * h.nsz + (bz >> 2);
         vis = c.max_depth > 0.0 && ((sb_flags[sb >> 5] >> (sb & 31)) & 1u) && brick_visible(f, c, bx, by, bz);

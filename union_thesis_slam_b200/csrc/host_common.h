@@ -124,7 +124,8 @@ struct FrameIO {
     FramePixel *px_slot[MAX_PREP] = {}; // prepared frames (depth + folded colour, 16 B per pixel)
     uint8_t *scratch_slot[MAX_PREP] = {};
     TilePyramid pyr_slot[MAX_PREP] = {};
-    size_t clear_bytes = 0;
+    unsigned frame_tag = 0;                     // tag of the last prepared frame (see FrameScratch); 0 is never used
+    unsigned next_tag() { return ++frame_tag ? frame_tag : ++frame_tag; }
     int slot = FRAME_SLOTS - 1; // scratch slot of the frame being issued (advanced by begin_kernels)
     // views of the current slot (after a frame: of the last frame issued)
     FramePixel *d_px = nullptr;
@@ -156,11 +157,9 @@ struct FrameIO {
     int ensure_px(int npix);
     int set_subs(int n);              // prepared frames per slot (drains the streams when it grows)
     static int prep_index(int slot, int sub) { return sub * FRAME_SLOTS + slot; }
-    int clear_sub(int sub);           // clears the scratch of prepared frame `sub` of the current slot (on `pre`)
     int release_upload_after_prep();  // the uploaded frame is consumed by the preparation kernel alone
     int ensure_tiles(int H, int W);   // (re)allocates fs + pyramid for this image size
-    // picks the frame's scratch slot, waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it,
-    // clears FrameScratch + pyramid levels 1..3
+    // picks the frame's scratch slot and waits (on `pre`) until the frame FRAME_SLOTS calls ago has left it
     int begin_kernels();
     int prepared();    // preparation kernels issued: `compute` waits for them
     int end_kernels(); // integrate issued: records timing, frees the scratch and upload slots

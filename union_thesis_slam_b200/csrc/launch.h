@@ -9,9 +9,12 @@ struct CullParams;
 struct BrickRef;
 struct FramePixel;
 
-// Reset by one cudaMemsetAsync at the start of every frame.
+// Per-frame scratch.  No memset per frame: k_prep_frame zeroes the counters (it is the first kernel of a frame's
+// chain and does not use them) and the maxima are TAGGED -- (frame tag << 32) | float bits, raised with a 64-bit
+// atomicMax -- so a value left by another frame simply reads as "no valid depth" (frame_max_depth()).  One launch less
+// on the preparation stream per frame, which at 8 ranks is close to the critical path (profiles/r2_dense_ab.md).
 struct FrameScratch {
-    unsigned int max_depth_bits; // float bits of the largest valid depth (rounded up)
+    unsigned long long max_depth_tagged; // tag << 32 | float bits of the largest valid depth (rounded up)
     int vis_count;               // entries in the visible-brick list
     unsigned long long updated;  // voxels updated by this frame
     int cand_count;              // hash: candidate keys emitted by the ray walk (after dedup)
@@ -43,10 +46,11 @@ static inline int sheets_of(int nbx, int rank, int world)
 #define DENSE_MAX_BATCH 4 // frames applied to a brick in one visit (temporal blocking)
 
 // Max valid depth per pixel tile, 4 levels: 8, 16, 32, 64 px tiles (0 = no valid pixel in the tile).
-// Level 0 is written by prep_frame, levels 1..3 by atomicMax from the same kernel (they are
-// cleared together with FrameScratch at the start of every frame).
+// Level 0 is plain floats, fully rewritten by prep_frame every frame; levels 1..3 are tagged 64-bit words raised by
+// atomicMax from the same kernel (see FrameScratch) and read through pyramid_depth().
 struct TilePyramid {
-    float *level[4];
+    float *level0;
+    unsigned long long *up[3];
     int tx[4], ty[4];
 };
 
@@ -75,7 +79,7 @@ struct Totals {
 
 void launch_fill_bricks(float *bricks, size_t nbricks, int sm_count, cudaStream_t s);
 void launch_prep_frame(const uint8_t *rgb, const double *depth, FramePixel *px, FrameScratch *fs,
-                       const TilePyramid &pyr, int H, int W, cudaStream_t s);
+                       const TilePyramid &pyr, int H, int W, unsigned tag, cudaStream_t s);
 void launch_cull_bricks(const FrameParams &f, const CullParams &c, int nlbx, int nby, int nbz, int rank, int world,
                         int classes, BrickRef *lists, size_t class_cap, FrameScratch *fs, cudaStream_t s);
 void launch_depth_u16(const uint16_t *raw, double *depth, int npix, double scale, int invalid_raw, cudaStream_t s);
