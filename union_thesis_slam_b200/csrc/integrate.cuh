@@ -82,13 +82,6 @@ __device__ __forceinline__ bool quad_depth_test(const FrameParams &f, const doub
     return (cls[0] | cls[1] | cls[2] | cls[3]) != 0;
 }
 
-// Read-modify-write of the four voxels in registers (Appendix A steps 7-9).  Returns whether any
-// voxel's tsdf changed (only then does the tsdf plane need to be stored: free space seen with
-// tsdf still 1 keeps it at 1 exactly).
-//   Fast path per voxel (update_voxel_fast's conditions): free space (diff >= trunc, dist == 1) seen
-//   with tsdf still 1 and a weight whose float32 add is exact; everything else (truncation band,
-//   re-observed surface voxels, unusual weights) goes through update_voxel_slow.
-//   The four colour blends sit behind ONE branch (skip_colour is per thread, not per voxel).
 // Out of line on purpose: inlined, the compiler runs the test speculatively for every quad; as a call
 // it costs nothing until weights are large enough for it to have a chance (see quad_update).
 static __device__ __noinline__ bool colour_converged4_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t n0,
@@ -100,33 +93,33 @@ static __device__ __noinline__ bool colour_converged4_call(uint32_t c0, uint32_t
     return colour_converged4(c, n, w);
 }
 
-#ifndef QUAD_CLS
-#define QUAD_CLS 0
-#endif
-#ifndef CONV_NOINLINE
-#define CONV_NOINLINE 1
-#endif
+// Read-modify-write of the four voxels in registers (Appendix A steps 7-9).  Returns whether any
+// voxel's tsdf changed (only then does the tsdf plane need to be stored: free space seen with
+// tsdf still 1 keeps it at 1 exactly).
+//   Fast path per voxel: free space (diff >= trunc, so dist == 1) seen with tsdf still 1 and a weight whose
+//   float32 add is exact -- then (w*1 + obs*1) / w_new is exactly 1 and f32(f64(w) + obs) == w + obs_f, so
+//   only weight and colour change.  UNIT_W (every frame so far had obs_weight == 1, weights are integers):
+//   exact for w < 32767; otherwise the two-sum identity checks the add.  Everything else (truncation band,
+//   re-observed surface voxels, unusual weights) goes through update_voxel_slow.
+//   The four colour blends sit behind ONE branch (skip_colour is per thread, not per voxel).
 template <bool UNIT_W>
-__device__ __forceinline__ bool quad_update(const FrameParams &f, const double diff[4], const int cls_[4],
-                                            const uint32_t nc[4], float t[4], float w[4], uint32_t c[4])
+__device__ __forceinline__ bool quad_update(const FrameParams &f, const double diff[4], const uint32_t nc[4], float t[4],
+                                            float w[4], uint32_t c[4])
 {
-#if QUAD_CLS
-    const int *cls = cls_;
-#else
-    // predicates straight from the float64 comparisons (the integer class only feeds quad_count)
-    struct { bool p, f; } k[4];
+    // predicates straight from the float64 comparisons (measured cheaper than carrying the integer class of
+    // quad_depth_test through the update, profiles/r2_dense_ab.md)
+    bool pass[4], free_space[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { k[e].p = diff[e] >= f.neg_trunc; k[e].f = diff[e] >= f.trunc; }
-    struct Cls { bool p, f; __device__ bool operator==(int v) const { return v == 2 ? f : (v == 1 ? (p && !f) : !p); }
-                 __device__ bool operator!=(int v) const { return !(*this == v); } __device__ operator bool() const { return p; } };
-    const Cls cls[4] = {{k[0].p, k[0].f}, {k[1].p, k[1].f}, {k[2].p, k[2].f}, {k[3].p, k[3].f}};
-#endif
+    for (int e = 0; e < 4; ++e) {
+        pass[e] = diff[e] >= f.neg_trunc;
+        free_space[e] = diff[e] >= f.trunc;
+    }
     float wn[4];
     bool ok[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         wn[e] = __fadd_rn(w[e], UNIT_W ? 1.0f : f.obs_f);
-        ok[e] = cls[e] == 2 && t[e] == 1.0f;
+        ok[e] = free_space[e] && t[e] == 1.0f;
         if (UNIT_W)
             ok[e] = ok[e] && w[e] < 32767.0f; // integer weights: w + 1 exact, and blend_color_unit's range
         else
@@ -141,14 +134,10 @@ __device__ __forceinline__ bool quad_update(const FrameParams &f, const double d
         float wq[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            ncq[e] = cls[e] ? nc[e] : c[e];
-            wq[e] = cls[e] ? w[e] : 1024.0f;
+            ncq[e] = pass[e] ? nc[e] : c[e];
+            wq[e] = pass[e] ? w[e] : 1024.0f;
         }
-#if CONV_NOINLINE
         skip_colour = colour_converged4_call(c[0], c[1], c[2], c[3], ncq[0], ncq[1], ncq[2], ncq[3], wq[0], wq[1], wq[2], wq[3]);
-#else
-        skip_colour = colour_converged4(c, ncq, wq);
-#endif
     }
     uint32_t cn[4] = {c[0], c[1], c[2], c[3]};
     if (!skip_colour) {
@@ -160,7 +149,7 @@ __device__ __forceinline__ bool quad_update(const FrameParams &f, const double d
     bool slow[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        slow[e] = cls[e] != 0 && !ok[e];
+        slow[e] = pass[e] && !ok[e];
         if (ok[e]) { w[e] = wn[e]; c[e] = cn[e]; }
     }
     const bool any_slow = slow[0] || slow[1] || slow[2] || slow[3];
@@ -169,7 +158,7 @@ __device__ __forceinline__ bool quad_update(const FrameParams &f, const double d
         for (int e = 0; e < 4; ++e)
             if (slow[e]) {
                 // grid_fusion.py:286: min(1, diff/trunc); the quotient is >= 1 exactly when diff >= trunc
-                const double dist = cls[e] == 1 ? fmin(1.0, __ddiv_rn(diff[e], f.trunc)) : 1.0;
+                const double dist = free_space[e] ? 1.0 : fmin(1.0, __ddiv_rn(diff[e], f.trunc));
                 Voxel vin;
                 vin.tsdf = t[e]; vin.wgt = w[e]; vin.col = c[e];
                 const Voxel vo = update_voxel_slow(vin, dist, nc[e], f.obs, f.obs_f);
@@ -230,7 +219,7 @@ __device__ __forceinline__ unsigned integrate_quad(const FrameParams &f, double 
     if (PROBE) return npass;
     float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
     uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
-    if (quad_update<UNIT_W>(f, diff, cls, nc, t, w, c))
+    if (quad_update<UNIT_W>(f, diff, nc, t, w, c))
         __stcs(reinterpret_cast<float4 *>(rec), make_float4(t[0], t[1], t[2], t[3]));
     __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), make_float4(w[0], w[1], w[2], w[3]));
     __stcs(reinterpret_cast<uint4 *>(rec + 2 * BRICK_VOX), make_uint4(c[0], c[1], c[2], c[3]));
@@ -319,7 +308,7 @@ __device__ __forceinline__ unsigned integrate_quad_slot(const FrameParams &f, do
     const uint4 C4 = *reinterpret_cast<const uint4 *>(slot + 2 * INTEGRATE_THREADS);
     float t[4] = {T4.x, T4.y, T4.z, T4.w}, w[4] = {W4.x, W4.y, W4.z, W4.w};
     uint32_t c[4] = {C4.x, C4.y, C4.z, C4.w};
-    const bool tsdf_changed = quad_update<UNIT_W>(f, diff, cls, nc, t, w, c);
+    const bool tsdf_changed = quad_update<UNIT_W>(f, diff, nc, t, w, c);
     if (FINAL) {
         if (tsdf_changed) __stcs(reinterpret_cast<float4 *>(rec), make_float4(t[0], t[1], t[2], t[3]));
         __stcs(reinterpret_cast<float4 *>(rec + BRICK_VOX), make_float4(w[0], w[1], w[2], w[3]));
