@@ -308,7 +308,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(1),
+        # the same workload description as the product arm prints at this N (the driver compares the two)
+        "config": dict(workload_config(int(os.environ.get("WORLD_SIZE", "1"))), frames_per_brick_visit=args.batch),
         "cpu_baseline": {k: v for k, v in r.items() if k not in ("seconds", "frames_per_s_sample")},
         "e2e": {"value": r["value"], "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": r["frames_per_s_sample"], "gpu_launches": 0,
