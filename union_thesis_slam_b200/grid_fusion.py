@@ -175,6 +175,9 @@ class TSDFVolume:
         return t.value
 
     def stats_wait(self, ticket):
+        """The snapshot of a stats_post() ticket (blocks until that snapshot has landed, not until the device is
+        idle).  ``updated_total`` is -1 in a snapshot: later frames may already be adding to the running total;
+        ``stats()`` reports it."""
         c = np.zeros(4, np.int64)
         _capi.check(self._lib.tsdf_grid_stats_wait(self._handle, int(ticket), _capi.ptr(c)))
         return dict(updated_last=int(c[0]), updated_total=int(c[1]), bricks_visited_last=int(c[2]),
