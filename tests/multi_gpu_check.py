@@ -45,6 +45,8 @@ def main():
     nblk = torch.tensor([ht.stats()["blocks"]], device="cuda")
     dist.all_reduce(nblk)
     want = len(oracle.block_set_from_weight(orc._weight_vol_cpu))
+    # the per-voxel view over the sharded map: entry count == voxels the oracle updated
+    ok_h = ok_h and ht.count_num_hash_entries() == int((orc._weight_vol_cpu > 0).sum())
     flag = torch.tensor([int(ok and ok_h and int(nblk.item()) == want)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -244,6 +244,7 @@ int FrameIO::ensure_tiles(int H, int W)
     CUDA_TRY(cudaStreamSynchronize(pre));
     CUDA_TRY(cudaStreamSynchronize(compute));
     { int rc_ = sync_side(); if (rc_) return rc_; }
+    CUDA_TRY(cudaStreamSynchronize(stat)); // a counter snapshot may still be reading the scratch that is about to go
     size_t off[4], total = 256; // FrameScratch lives in the first 256 bytes
     TilePyramid p{};
     for (int l = 1; l <= 3; ++l) {

@@ -261,9 +261,16 @@ class HashTable:
         return self.voxel_table.get_num_collisions() if (self._voxels is not None or self._per_voxel) else 0
 
     def count_voxels(self):
-        """Voxels with an entry among those written by integrate() (weight > 0), counted on the device."""
+        """Voxels with an entry among those written by integrate() (weight > 0), counted on the device; with
+        world_size > 1 the sum over the ranks' disjoint block sets."""
         n = C.c_int64()
         _capi.check(self._lib.vh_count_voxels(self._handle, C.byref(n)))
+        if self.world_size > 1:
+            import torch
+            import torch.distributed as tdist
+            t = torch.tensor([n.value], dtype=torch.int64, device=torch.device("cuda", self.device))
+            tdist.all_reduce(t, group=self._group)
+            return int(t.item())
         return n.value
 
     # -- occupancy metrics (reference hash_fusion.py:147-180) ------------------------------------
