@@ -394,25 +394,31 @@ def timed_device(D, vol, step, n, first, sampler=None):
     return ms, upd
 
 
-def e2e_loop(D, vol, call, n, first):
+E2E_DEPTH = 6  # steps whose result read-back may be outstanding while the host issues the next one
+
+
+def e2e_loop(D, vol, call, n, first, after=None):
     """End to end through the public API with HOST frames: every step uploads its frame (inside the
     integrate call) and reads a step result back.  The read-back is pipelined: step k posts its
     counters (stats_post: a 64-byte device->host copy into pinned memory behind the step's kernels) and
-    the host consumes step k-1's, so the upload of frame k+1 overlaps the integration of frame k; every
-    step's result has been read when the clock stops.  Returns (seconds max over ranks, updates)."""
+    the host consumes step k-E2E_DEPTH's, so the upload and preparation of the next frames overlap the
+    integration of frame k; every step's result has been read when the clock stops.  Returns (seconds max
+    over ranks, updates)."""
     vol.sync()
     D.barrier()
     t0 = time.perf_counter()
     upd = 0
-    prev = None
+    posted = []
     for i in range(n):
         call(first + i)
-        t = vol.stats_post()
-        if prev is not None:
-            upd += vol.stats_wait(prev)["updated_last"]
-        prev = t
-    upd += vol.stats_wait(prev)["updated_last"]
+        posted.append(vol.stats_post())
+        if len(posted) > E2E_DEPTH:
+            upd += vol.stats_wait(posted.pop(0))["updated_last"]
+    for t in posted:
+        upd += vol.stats_wait(t)["updated_last"]
     vol.sync()
+    if after:
+        after()
     D.barrier()
     return D.max(time.perf_counter() - t0), D.sum(float(upd))
 
@@ -502,12 +508,26 @@ def run_b200(args):
     # Each end-to-end variant runs on a FRESH volume with the same warm-up frames and the same timed frames as
     # the device-timed region above, so its figure is directly comparable with `value` (a frame costs more
     # once its voxels have been observed before: more of them sit in the truncation band).
+    # From two ranks on, the frame crosses PCIe once (on rank step % world) and is fanned out over NVLink
+    # peer memory (dist.FrameFanout); "per_rank_upload" keeps the figure of every rank uploading every
+    # frame itself, which is bounded by the host's PCIe complex.
+    from union_thesis_slam_b200 import dist as tdist
+    fan_error = []
+
     def e2e_variant(kind):
         v = grid_fusion.TSDFVolume(room.copy(), VOXEL, rank=rank, world_size=world, device=local)
+        fan = None
+        if world > 1 and kind in ("f64", "u16") and not fan_error:
+            try:
+                fan = tdist.FrameFanout(v, IM_H, IM_W, raw_depth=(kind == "u16"), depth_scale=1000., invalid_raw=65535)
+            except Exception as exc:  # e.g. CUDA IPC not permitted in this container: every rank uploads for itself
+                fan_error.append(repr(exc))
 
         def call(i):
             c, d, p, raw = h_frames[i % N_FRAMES][:4]
-            if kind == "u16":
+            if fan is not None:
+                fan.integrate(c, raw if kind == "u16" else d, K, p, obs_weight=1.)
+            elif kind == "u16":
                 v.integrate_raw(c, raw, K, p, obs_weight=1., depth_scale=1000., invalid_raw=65535)
             else:
                 v.integrate(c, d, K, p, obs_weight=1.)
@@ -526,7 +546,9 @@ def run_b200(args):
             D.barrier()
             res = D.max(time.perf_counter() - t0), D.sum(float(n_upd))
         else:
-            res = e2e_loop(D, v, call, args.steps, args.warmup)
+            res = e2e_loop(D, v, call, args.steps, args.warmup, after=fan.drain if fan else None)
+        if fan is not None:
+            fan.close()
         v.close()
         return res
 
@@ -534,16 +556,32 @@ def run_b200(args):
     e2e_s, e2e_upd = e2e_variant("f64")
     raw_s, raw_upd = e2e_variant("u16")
     blk_s, blk_upd = e2e_variant("blocking")
+    fan_note = "" if world == 1 else (
+        " -- through dist.FrameFanout: frame k is uploaded by rank k %% %d alone and pulled by every peer's copy engine into "
+        "its own ring slot over NVLink (%d x the frame's bytes per step), every rank integrates its own sheets" % (world, world - 1))
     e2e = {"value": e2e_upd / e2e_s, "unit": "voxel-updates/s", "h2d_bytes_per_step": npix * (8 + 3),
-           "d2h_bytes_per_step": 64, "frames_per_s": args.steps / e2e_s,
+           "d2h_bytes_per_step": 64 * world, "frames_per_s": args.steps / e2e_s,
            "api": "TSDFVolume.integrate(color, depth f64, K, pose) every step from pinned host buffers (3.38 MB H2D "
-                  "inside the call) + stats_post(); the 64-byte counter block of step k-1 is read (stats_wait) "
-                  "while step k runs, all of them before the clock stops",
+                  "inside the call) + stats_post(); the 64-byte counter block of step k-%d is read (stats_wait) "
+                  "while step k runs, all of them before the clock stops%s" % (E2E_DEPTH, fan_note),
            "raw_u16": {"value": raw_upd / raw_s, "frames_per_s": args.steps / raw_s,
                        "h2d_bytes_per_step": npix * (2 + 3),
                        "api": "TSDFVolume.integrate_raw: the sensor's uint16 depth, divided and masked on the device"},
            "blocking_read": {"value": blk_upd / blk_s, "frames_per_s": args.steps / blk_s,
-                             "api": "integrate() + stats() per step: the host waits for the device every step"}}
+                             "h2d_bytes_per_step": npix * (8 + 3) * world,
+                             "api": "integrate() + stats() per step: the host waits for the device every step"
+                                    + (" (every rank uploads the frame itself)" if world > 1 else "")}}
+    if fan_error:
+        e2e["fanout_error"] = fan_error[0]
+        e2e["api"] = e2e["api"].replace(fan_note, " -- every rank uploads the frame itself (fan-out unavailable)")
+        e2e["h2d_bytes_per_step"] = npix * (8 + 3) * world
+    elif world > 1:
+        e2e["nvlink_bytes_per_step"] = npix * (8 + 3) * (world - 1)
+    if world > 1:
+        pr_s, pr_upd = e2e_variant("per_rank")
+        e2e["per_rank_upload"] = {"value": pr_upd / pr_s, "frames_per_s": args.steps / pr_s,
+                                  "h2d_bytes_per_step": npix * (8 + 3) * world,
+                                  "api": "every rank calls TSDFVolume.integrate with the host frame itself (no fan-out)"}
     clocks = sampler.stop() if sampler else None
 
     line = {
@@ -708,13 +746,26 @@ def bench_hash(args, D):
         pc, pd = torch.from_numpy(c).pin_memory(), torch.from_numpy(d).pin_memory()
         h_frames.append((pc.numpy(), pd.numpy(), p, pc, pd))
 
+    fan = None
+    if world > 1:  # the frame is uploaded once and fanned out over NVLink (dist.FrameFanout)
+        from union_thesis_slam_b200 import dist as tdist
+        try:
+            fan = tdist.FrameFanout(ht, HASH_H, HASH_W)
+        except Exception:
+            fan = None
+
     def call(i):
         c, d, p = h_frames[i % N_FRAMES][:3]
-        ht.integrate(c, d, K, p, obs_weight=1.)
+        if fan is not None:
+            fan.integrate(c, d, K, p, obs_weight=1.)
+        else:
+            ht.integrate(c, d, K, p, obs_weight=1.)
 
     for i in range(2):
         call(i)
-    e2e_s, e2e_upd = e2e_loop(D, ht, call, steps, 2)
+    e2e_s, e2e_upd = e2e_loop(D, ht, call, steps, 2, after=fan.drain if fan else None)
+    if fan is not None:
+        fan.close()
     out = {"metric": "tsdf_voxel_updates_per_s", "value": upd / wall, "unit": "voxel-updates/s", "n_gpus": world,
            "blocks_allocated_all_ranks": int(blocks_all),
            "frames_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps,
@@ -729,9 +780,14 @@ def bench_hash(args, D):
                                        "compaction, integrate",
                         "traffic": None},
            "e2e": {"value": e2e_upd / e2e_s, "unit": "voxel-updates/s", "frames_per_s": steps / e2e_s,
-                   "h2d_bytes_per_step": HASH_W * HASH_H * (8 + 3), "d2h_bytes_per_step": 96,
+                   "h2d_bytes_per_step": HASH_W * HASH_H * (8 + 3) * (1 if fan is not None else world),
+                   "d2h_bytes_per_step": 96 * world,
+                   "nvlink_bytes_per_step": HASH_W * HASH_H * (8 + 3) * (world - 1) if fan is not None else 0,
                    "api": "HashTable.integrate(color, depth f64, K, pose) from pinned host buffers + stats_post(); "
-                          "step k-1's counters are read while step k runs"}}
+                          "step k-%d's counters are read while step k runs%s" % (
+                              E2E_DEPTH, "; every rank uploads the frame itself" if fan is None else
+                              "; frame k is uploaded by rank k % world alone and pulled by the peers' copy engines "
+                              "over NVLink (dist.FrameFanout)")}}
     tf = os.path.join(ROOT, "profiles", "hash_traffic.json")
     if os.path.exists(tf):
         with open(tf) as fh:

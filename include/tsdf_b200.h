@@ -74,6 +74,17 @@ int tsdf_grid_integrate_u16(tsdf_grid *g, const uint8_t *rgb, const uint16_t *de
 /* Same, frame already resident in device memory (throughput runs; no H2D inside). */
 int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, const double *d_depth, int H, int W,
                                const double K[9], const double Tinv[16], double obs_weight);
+/* Same for the sensor's raw uint16 depth resident in device memory (converted as in tsdf_grid_integrate_u16). */
+int tsdf_grid_integrate_device_u16(tsdf_grid *g, const uint8_t *d_rgb, const uint16_t *d_depth_raw, int H, int W,
+                                   const double K[9], const double Tinv[16], double obs_weight, double depth_scale,
+                                   int invalid_raw);
+/* Frame fan-out (the "each frame's depth, colour and pose broadcast to all ranks" step of the multi-GPU scheme;
+ * the reference has no counterpart: grid_demo1.py:76-87 reads every frame in the one process it has).
+ * Declares that the device buffers passed to the NEXT tsdf_grid_integrate_device[_u16] call are being written
+ * by work already enqueued on the caller's CUDA stream `producer_stream` (an upload, an NCCL broadcast): the
+ * handle orders its preparation kernel after that work, and orders `producer_stream` after the kernel has
+ * consumed the frame, so the caller may enqueue the next write into the same buffers at once.  No host wait. */
+int tsdf_grid_frame_source(tsdf_grid *g, void *producer_stream);
 
 /* TSDFVolume.get_volume (grid_fusion.py:316-320) plus the weight plane (_weight_vol_cpu).
  * Writes this rank's sheets, un-bricked, as C-order [nx_local][Y][Z] float32 host arrays; any
@@ -149,6 +160,11 @@ int vh_integrate_u16(tsdf_hash *h, const uint8_t *rgb, const uint16_t *depth_raw
                      const double Tinv[16], double obs_weight, double depth_scale, int invalid_raw);
 int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, int H, int W,
                         const double K[9], const double Tinv[16], double obs_weight);
+int vh_integrate_device_u16(tsdf_hash *h, const uint8_t *d_rgb, const uint16_t *d_depth_raw, int H, int W,
+                            const double K[9], const double Tinv[16], double obs_weight, double depth_scale,
+                            int invalid_raw);
+/* As tsdf_grid_frame_source, for the hash map. */
+int vh_frame_source(tsdf_hash *h, void *producer_stream);
 
 /* HashTable.count_num_hash_entries / get_load_factor / get_num_collisions analogues
  * (hash_fusion.py:147-180).  stats[0] allocated blocks, [1] table keys (incl. keys whose block
@@ -263,6 +279,44 @@ int vbt_to_dense(tsdf_buckets *h, const int64_t dim[3], float *tsdf, float *colo
  * {bucket, slot, x, y, z, offset bucket, offset slot} (-1, -1 = empty offset); voxels (may be
  * NULL) [count][3] = (sdf, colour, weight), NaN sdf for an entry stored without a voxel. */
 int vbt_dump(tsdf_buckets *h, int64_t capacity, int64_t *count, int64_t *rows, double *voxels);
+
+/* ---- frame fan-out over NVLink peer memory (multi-GPU, one process per GPU) -------------------------------
+ * The "each frame's depth, colour and pose broadcast to all ranks" step of the multi-GPU scheme; the reference is
+ * one process and reads every frame itself (grid_fusion_demos/grid_demo1.py:76-87), so there is nothing it binds
+ * here -- a multi-process host of the reference would.  A frame is uploaded once, on its source rank, into a ring
+ * slot of that rank's arena; every peer's copy engine pulls it over NVLink from there (CUDA IPC mappings) into the
+ * same slot of its own arena.  "Staged" and "pulled" are sequence-number flags in the arenas, written by peer
+ * stores and waited for on the device, never on the host.
+ *
+ * create -> export (64-byte handle) -> [the caller all-gathers the handles] -> connect (handles of all ranks, in rank
+ * order; the own entry is ignored).  Per frame `seq` (0, 1, 2, ... on every rank alike), source rank `src`:
+ *   src only : tsdf_fanout_push(seq, host depth, host colour)      -- the slot is seq % slots
+ *   all ranks: tsdf_fanout_acquire(seq, src, ...) -> device pointers of the frame and the stream they arrive on;
+ *              tsdf_grid_frame_source / vh_frame_source(that stream); tsdf_grid_integrate_device[_u16] / vh_...;
+ *              tsdf_fanout_release(seq)                            -- marks the slot's consumption on that stream
+ * Pinned host buffers given to push are read asynchronously: they must stay unchanged until the rank's next push or
+ * tsdf_fanout_drain returns.  drain also reports a peer that failed to deliver / consume within the time-out
+ * (default 20 s).  Before destroy the caller synchronises the ranks (peers write into this rank's arena). */
+typedef struct tsdf_fanout tsdf_fanout;
+int tsdf_fanout_create(int device, int rank, int world, int64_t slot_bytes, int slots, tsdf_fanout **out);
+int tsdf_fanout_export(tsdf_fanout *f, uint8_t handle[64]);
+int tsdf_fanout_connect(tsdf_fanout *f, const uint8_t *handles /* [world][64] */);
+/* depth goes to offset 0 of the slot, colour to rgb_offset (>= depth_bytes). */
+int tsdf_fanout_push(tsdf_fanout *f, int64_t seq, const void *depth, int64_t depth_bytes, const void *rgb,
+                     int64_t rgb_bytes, int64_t rgb_offset);
+/* frame_bytes = rgb_offset + rgb_bytes: what a non-source rank pulls from the source's slot. */
+int tsdf_fanout_acquire(tsdf_fanout *f, int64_t seq, int src, int64_t frame_bytes, int64_t rgb_offset, void **d_depth,
+                        void **d_rgb, void **stream);
+int tsdf_fanout_release(tsdf_fanout *f, int64_t seq);
+/* The per-frame sequence above in one call, for a dense grid (hash == NULL) or a hash map (grid == NULL): push if
+ * src is this rank (depth: float64 metres, or raw uint16 with raw_u16 != 0; colour at the 256-byte-rounded offset
+ * behind it), acquire, frame_source, integrate_device[_u16], release.  depth / rgb are read on the source only. */
+int tsdf_fanout_integrate(tsdf_fanout *f, tsdf_grid *grid, tsdf_hash *hash, int64_t seq, int src, const void *depth,
+                          const void *rgb, int H, int W, int raw_u16, const double K[9], const double Tinv[16],
+                          double obs_weight, double depth_scale, int invalid_raw);
+int tsdf_fanout_drain(tsdf_fanout *f);
+int tsdf_fanout_set_timeout(tsdf_fanout *f, double seconds);
+int tsdf_fanout_destroy(tsdf_fanout *f);
 
 #ifdef __cplusplus
 }

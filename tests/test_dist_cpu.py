@@ -158,3 +158,72 @@ def test_block_list_gather_world3_with_an_empty_rank():
     res = _spawn(_block_list_job, 3)
     lens = {res[r][0] for r in range(3)}
     assert len(lens) == 1 and all(res[r][0] < res[r][4] for r in range(3))  # the last rank's blocks are missing everywhere
+
+
+class _RecordingMap:
+    """Stands in for a rank's TSDFVolume / HashTable: keeps what the fan-out hands to integrate_device."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world_size, self.device = rank, world, 0
+        self.got = []
+
+    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1., producer_stream=None):
+        assert producer_stream is None  # host memory: nothing to order
+        self.got.append((d_rgb.numpy().copy().reshape(im_h, im_w, 3), d_depth.numpy().copy().view(np.float64).reshape(im_h, im_w),
+                         np.array(tinv), float(obs_weight)))
+
+    def integrate_device_raw(self, d_rgb, d_raw, im_h, im_w, cam_intr, tinv, obs_weight=1., depth_scale=1000.,
+                             invalid_raw=65535, producer_stream=None):
+        self.got.append((d_rgb.numpy().copy().reshape(im_h, im_w, 3), d_raw.numpy().copy().view(np.uint16).reshape(im_h, im_w),
+                         np.array(tinv), (float(depth_scale), int(invalid_raw))))
+
+
+def _fanout_frames(n, h=6, w=10):
+    rng = np.random.default_rng(11)
+    out = []
+    for i in range(n):
+        pose = np.eye(4)
+        pose[:3, 3] = rng.normal(size=3)
+        out.append((rng.integers(0, 256, (h, w, 3), dtype=np.uint8), rng.uniform(0.0, 4.0, (h, w)),
+                    rng.integers(0, 65536, (h, w)).astype(np.uint16), pose))
+    return out
+
+
+def _fanout_worker(rank, world):
+    frs = _fanout_frames(5)
+    K = np.eye(3)
+    res = {}
+    for raw in (False, True):
+        m = _RecordingMap(rank, world)
+        fan = tdist.FrameFanout(m, 6, 10, raw_depth=raw, depth_scale=500., invalid_raw=7, device="cpu")
+        assert fan.payload_bytes() == 6 * 10 * ((2 if raw else 8) + 3)
+        for i, (c, d, r, p) in enumerate(frs):
+            mine = fan.source_of(i) == rank
+            # only the frame's source rank holds its images
+            fan.integrate(c if mine else None, (r if raw else d) if mine else None, K, p, obs_weight=1.0 + i)
+        fan.drain()
+        res[raw] = m.got
+    with pytest.raises(ValueError):  # the source rank must supply the images
+        tdist.FrameFanout(_RecordingMap(rank, world), 6, 10, device="cpu").integrate(None, None, K, np.eye(4), src=rank)
+    return res
+
+
+def test_frame_fanout_delivers_every_frame_to_every_rank_world2():
+    frs = _fanout_frames(5)
+    out = _spawn(_fanout_worker, world=2)
+    for rank in (0, 1):
+        for raw in (False, True):
+            got = out[rank][raw]
+            assert len(got) == len(frs)
+            for i, (c, d, r, p) in enumerate(frs):
+                assert np.array_equal(got[i][0], c)
+                assert np.array_equal(got[i][1], r if raw else d)
+                assert np.array_equal(got[i][2], np.linalg.inv(p))
+                assert got[i][3] == ((500.0, 7) if raw else 1.0 + i)
+
+
+def test_frame_fanout_rotates_the_upload_rank():
+    fan = tdist.FrameFanout(_RecordingMap(1, 4), 4, 4, device="cpu")
+    assert [fan.source_of(i) for i in range(9)] == [0, 1, 2, 3, 0, 1, 2, 3, 0]
+    with pytest.raises(ValueError):
+        fan.integrate(None, None, np.eye(3), np.eye(4), src=4)

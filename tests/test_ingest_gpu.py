@@ -37,6 +37,51 @@ def test_raw_uint16_depth_ingest_is_bit_identical():
     assert a.stats()["updated_total"] == b.stats()["updated_total"] > 0
 
 
+def test_frame_fanout_on_one_rank_equals_the_direct_calls():
+    """dist.FrameFanout (upload on the fan-out's stream into a ring of device buffers, integrate from the resident
+    copy, stream-ordered both ways) == integrate()/integrate_raw() with host frames; a ring of 2 buffers over 6
+    frames makes every buffer be overwritten while earlier frames are still in flight."""
+    import torch
+    from union_thesis_slam_b200 import dist as tdist, grid_fusion, hash_fusion
+    K = frames.intrinsics()
+    bounds = np.array(scenes.CONFIG1_BOUNDS)
+    idx = (0, 1, 2, 3, 500, 999)
+    loaded = []
+    for i in idx:
+        c, d, p = frames.load_frame(i)
+        raw = cv2.imread(os.path.join(frames.FRAMES_DIR, "frame-%06d.depth.png" % i), -1)
+        loaded.append((c, d, raw, p))
+    h, w = loaded[0][1].shape
+    for raw_mode, transport in ((False, "peer"), (True, "peer"), (False, "collective")):
+        ref = grid_fusion.TSDFVolume(bounds.copy(), 0.04)
+        vol = grid_fusion.TSDFVolume(bounds.copy(), 0.04)
+        ht = hash_fusion.HashTable(bounds.copy(), 0.04, map_size=1 << 15)
+        fan_v = tdist.FrameFanout(vol, h, w, raw_depth=raw_mode, slots=2, transport=transport)
+        # the hash map behind a plain object: the fan-out then drives push / acquire / frame_source / release itself
+        # instead of the one-call native step it uses for the product's own classes
+        class Wrapped:
+            rank, world_size, device = ht.rank, ht.world_size, ht.device
+            integrate_device, integrate_device_raw, sync = ht.integrate_device, ht.integrate_device_raw, ht.sync
+        fan_h = tdist.FrameFanout(Wrapped if raw_mode else ht, h, w, raw_depth=raw_mode, slots=2, transport=transport)
+        for k, (c, d, raw, p) in enumerate(loaded):
+            obs = 1.0 if k < 4 else 2.0
+            ref.integrate(c, d, K, p, obs_weight=obs)
+            # pinned source buffers: the copy engine reads them after the call returned
+            pc = torch.from_numpy(c).pin_memory().numpy()
+            pd = torch.from_numpy(raw if raw_mode else d).pin_memory().numpy()
+            fan_v.integrate(pc, pd, K, p, obs_weight=obs)
+            fan_h.integrate(c, raw if raw_mode else d, K, p, obs_weight=obs)
+        fan_v.drain(); fan_h.drain()
+        t0, c0 = ref.get_volume()
+        t1, c1 = vol.get_volume()
+        t2, w2, c2 = ht.get_volume_with_weight()
+        assert np.array_equal(t0, t1) and np.array_equal(c0, c1) and np.array_equal(ref._weight_vol_cpu, vol._weight_vol_cpu)
+        assert np.array_equal(t0, t2) and np.array_equal(c0, c2) and np.array_equal(ref._weight_vol_cpu, w2)
+        assert ref.stats()["updated_total"] == vol.stats()["updated_total"] == ht.stats()["updated_total"] > 0
+        for x in (fan_v, fan_h, ref, vol, ht):
+            x.close()
+
+
 def test_demo_protocol_on_fixture_frames(tmp_path, capsys):
     """The reference demos' protocol (bounds pass, integrate loop, FPS, mesh + point cloud) runs
     unchanged against the drop-in modules; dense and hash agree."""

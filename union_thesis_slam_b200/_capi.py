@@ -28,6 +28,8 @@ SYMBOLS = [
     ("tsdf_grid_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("tsdf_grid_integrate_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
     ("tsdf_grid_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
+    ("tsdf_grid_integrate_device_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
+    ("tsdf_grid_frame_source", _i, [_p, _p]),
     ("tsdf_grid_download", _i, [_p, _p, _p, _p]),
     ("tsdf_grid_download_device", _i, [_p, _p, _p, _p]),
     ("tsdf_grid_local_x", _i, [_p, _p, _p]),
@@ -46,6 +48,18 @@ SYMBOLS = [
     ("vh_integrate", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
     ("vh_integrate_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
     ("vh_integrate_device", _i, [_p, _p, _p, _i, _i, _p, _p, _d]),
+    ("vh_integrate_device_u16", _i, [_p, _p, _p, _i, _i, _p, _p, _d, _d, _i]),
+    ("vh_frame_source", _i, [_p, _p]),
+    ("tsdf_fanout_create", _i, [_i, _i, _i, _i64, _i, _pp]),
+    ("tsdf_fanout_export", _i, [_p, _p]),
+    ("tsdf_fanout_connect", _i, [_p, _p]),
+    ("tsdf_fanout_push", _i, [_p, _i64, _p, _i64, _p, _i64, _i64]),
+    ("tsdf_fanout_acquire", _i, [_p, _i64, _i, _i64, _i64, _pp, _pp, _pp]),
+    ("tsdf_fanout_release", _i, [_p, _i64]),
+    ("tsdf_fanout_integrate", _i, [_p, _p, _p, _i64, _i, _p, _p, _i, _i, _i, _p, _p, _d, _d, _i]),
+    ("tsdf_fanout_drain", _i, [_p]),
+    ("tsdf_fanout_set_timeout", _i, [_p, _d]),
+    ("tsdf_fanout_destroy", _i, [_p]),
     ("vh_stats", _i, [_p, _p]),
     ("vh_num_blocks", _i, [_p, _p]),
     ("vh_export_blocks_device", _i, [_p, _i64, _p, _p, _p]),
@@ -115,8 +129,8 @@ def check(status):
 
 def ptr(a):
     """void* of a numpy array, a torch tensor (data_ptr) or None."""
-    if a is None:
-        return None
+    if a is None or isinstance(a, int):  # an int is a raw address already
+        return a
     if isinstance(a, np.ndarray):
         return a.ctypes.data  # plain int: accepted for c_void_p parameters, cheaper than data_as()
     if hasattr(a, "data_ptr"):

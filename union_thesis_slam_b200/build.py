@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsdf_b200.so")
-SOURCES = ["capi_grid.cu", "dense_kernels.cu", "capi_hash.cu", "hash_kernels.cu", "mesh_kernels.cu", "bucket_kernels.cu"]
+SOURCES = ["capi_grid.cu", "dense_kernels.cu", "capi_hash.cu", "hash_kernels.cu", "mesh_kernels.cu", "bucket_kernels.cu", "capi_fanout.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     # the arithmetic contract is spelled out with explicit intrinsics; never let nvcc fuse on its own

@@ -168,6 +168,8 @@ int FrameIO::init()
     CUDA_TRY(cudaEventCreate(&k_begin));
     CUDA_TRY(cudaEventCreate(&k_end));
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&k_mark[i]));
+    CUDA_TRY(cudaEventCreateWithFlags(&ext_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ext_consumed, cudaEventDisableTiming));
     return TSDF_OK;
 }
 
@@ -235,6 +237,35 @@ int FrameIO::release_upload_after_prep()
         CUDA_TRY(cudaEventRecord(slot_free[cur], pre));
         cur = -1;
     }
+    if (ext) { // the caller's producer stream may reuse the frame's buffers from here on
+        CUDA_TRY(cudaEventRecord(ext_consumed, pre));
+        CUDA_TRY(cudaStreamWaitEvent(ext, ext_consumed, 0));
+        ext = nullptr;
+    }
+    return TSDF_OK;
+}
+
+int FrameIO::adopt(cudaStream_t producer)
+{
+    CUDA_TRY(cudaEventRecord(ext_ready, producer));
+    CUDA_TRY(cudaStreamWaitEvent(pre, ext_ready, 0));
+    ext = producer;
+    return TSDF_OK;
+}
+
+int FrameIO::convert_u16(const uint16_t *d_raw, int npix, double depth_scale, int invalid_raw, const double **d_depth_out)
+{
+    int rc = ensure(npix);
+    if (rc) return rc;
+    const int s = next;
+    next = (next + 1) % FRAME_SLOTS;
+    // the slot's float64 image was last read by the preparation kernel FRAME_SLOTS frames ago
+    CUDA_TRY(cudaStreamWaitEvent(pre, slot_free[s], 0));
+    for (int k = 0; k < side_used; ++k) CUDA_TRY(cudaStreamWaitEvent(pre, side_slot_free[k][s], 0));
+    launch_depth_u16(d_raw, d_depth[s], npix, depth_scale, invalid_raw, pre);
+    CUDA_TRY(cudaGetLastError());
+    cur = s;
+    *d_depth_out = d_depth[s];
     return TSDF_OK;
 }
 
@@ -504,6 +535,8 @@ void FrameIO::release()
         if (k_mark[i]) cudaEventDestroy(k_mark[i]);
     if (k_begin) cudaEventDestroy(k_begin);
     if (k_end) cudaEventDestroy(k_end);
+    if (ext_ready) cudaEventDestroy(ext_ready);
+    if (ext_consumed) cudaEventDestroy(ext_consumed);
     if (compute) cudaStreamDestroy(compute);
     for (int k = 0; k < MAX_SIDE; ++k) {
         if (side_end[k]) cudaEventDestroy(side_end[k]);
@@ -682,14 +715,13 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
         tsdf_set_error("too many bricks per rank (%zu)", g->nbricks);
         return TSDF_ERR_BAD_ARG;
     }
-    static_assert(FRAME_SLOTS == 3, "vis_list allocation below assumes three frame slots");
     cudaError_t e;
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
-    if ((e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list[0], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list[1], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&g->vis_list[2], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&g->tot, sizeof(Totals))) != cudaSuccess) {
+    e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float));
+    for (int i = 0; i < FRAME_SLOTS && e == cudaSuccess; ++i)
+        e = cudaMalloc(&g->vis_list[i], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef));
+    if (e == cudaSuccess) e = cudaMalloc(&g->tot, sizeof(Totals));
+    if (e != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));
         cudaGetLastError();
         grid_free(g);
@@ -832,6 +864,29 @@ extern "C" int tsdf_grid_integrate_device(tsdf_grid *g, const uint8_t *d_rgb, co
     int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
     if (rc) return rc;
     return grid_enqueue(g, d_rgb, d_depth, H, W, f, c);
+}
+
+extern "C" int tsdf_grid_integrate_device_u16(tsdf_grid *g, const uint8_t *d_rgb, const uint16_t *d_depth_raw, int H, int W,
+                                              const double K[9], const double Tinv[16], double obs_weight,
+                                              double depth_scale, int invalid_raw)
+{
+    BAD_ARG(!g || !d_rgb || !d_depth_raw, "NULL argument");
+    BAD_ARG(!(depth_scale > 0.0), "depth_scale must be positive");
+    CUDA_TRY(cudaSetDevice(g->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, g->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const double *d_depth;
+    if ((rc = g->io.convert_u16(d_depth_raw, H * W, depth_scale, invalid_raw, &d_depth))) return rc;
+    return grid_enqueue(g, d_rgb, d_depth, H, W, f, c);
+}
+
+extern "C" int tsdf_grid_frame_source(tsdf_grid *g, void *producer_stream)
+{
+    BAD_ARG(!g, "NULL handle");
+    CUDA_TRY(cudaSetDevice(g->device));
+    return g->io.adopt(static_cast<cudaStream_t>(producer_stream));
 }
 
 extern "C" int tsdf_grid_local_x(tsdf_grid *g, int64_t *n_x, int64_t *xs)

@@ -5,6 +5,13 @@
 
 #include "host_common.h"
 
+static cudaError_t alloc_lists(BrickRef *lists[FRAME_SLOTS], size_t cap)
+{
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < FRAME_SLOTS && e == cudaSuccess; ++i) e = cudaMalloc(&lists[i], cap * sizeof(BrickRef));
+    return e;
+}
+
 #define WALK_SB_PER_TILE 400.0 // the scan still wins at 83 super-blocks per tile (16x the scene's bounds, profiles/r2_hash_alloc.md)
 struct tsdf_hash {
     int device = 0, sm_count = 0, rank = 0, world = 1;
@@ -103,7 +110,6 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
     h->sb_words = ((size_t)d.nsx * d.nsy * d.nsz + 31) / 32;
     // a key exists at most once per block of the bounded grid: that bounds the visible list too
     const size_t list_cap = (size_t)std::min<int64_t>(S, (int64_t)d.nbx * d.nby * d.nbz);
-    static_assert(FRAME_SLOTS == 3, "vis_list allocation below assumes three frame slots");
     cudaError_t e;
     if ((e = cudaMalloc(&d.keys, S * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc(&d.vals, S * sizeof(uint32_t))) != cudaSuccess ||
@@ -114,9 +120,7 @@ extern "C" int vh_create(const int64_t dim[3], const float origin[3], double vox
         (e = cudaMalloc(&d.blocks, (size_t)heap_blocks * BRICK_FLOATS * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&d.known, known_words * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&h->sb_flags, h->sb_words * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list[0], list_cap * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list[1], list_cap * sizeof(BrickRef))) != cudaSuccess ||
-        (e = cudaMalloc(&h->vis_list[2], list_cap * sizeof(BrickRef))) != cudaSuccess ||
+        (e = alloc_lists(h->vis_list, list_cap)) != cudaSuccess ||
         (e = cudaMalloc(&h->tot, sizeof(Totals))) != cudaSuccess ||
         (e = cudaMalloc(&h->scratch_count, sizeof(int))) != cudaSuccess) {
         tsdf_set_error("device allocation failed (%lld slots, %lld blocks = %.2f GB): %s", (long long)S,
@@ -222,6 +226,7 @@ static int hash_run(tsdf_hash *h, const uint8_t *d_rgb, const double *d_depth, i
     c.tag = h->io.next_tag();
     launch_prep_frame(d_rgb, d_depth, h->io.d_px, h->io.fs, h->io.pyr, H, W, c.tag, s);
     CUDA_TRY(cudaGetLastError());
+    if ((rc = h->io.release_upload_after_prep())) return rc; // every later kernel reads the prepared pixels
     const double n_sb = (double)h->dev.nsx * h->dev.nsy * h->dev.nsz;
     const bool ray_walk = h->alloc_mode == 1 || (h->alloc_mode == 2 && n_sb > WALK_SB_PER_TILE * tiles_x * tiles_y);
     // the frame's visible-super-block bitmap: written by the walk or by the scan, read by refine and compaction
@@ -291,6 +296,29 @@ extern "C" int vh_integrate_device(tsdf_hash *h, const uint8_t *d_rgb, const dou
     int rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, obs_weight);
     if (rc) return rc;
     return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+}
+
+extern "C" int vh_integrate_device_u16(tsdf_hash *h, const uint8_t *d_rgb, const uint16_t *d_depth_raw, int H, int W,
+                                       const double K[9], const double Tinv[16], double obs_weight, double depth_scale,
+                                       int invalid_raw)
+{
+    BAD_ARG(!h || !d_rgb || !d_depth_raw, "NULL argument");
+    BAD_ARG(!(depth_scale > 0.0), "depth_scale must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    FrameParams f;
+    CullParams c;
+    int rc = make_frame_params(&f, &c, h->geom, H, W, K, Tinv, obs_weight);
+    if (rc) return rc;
+    const double *d_depth;
+    if ((rc = h->io.convert_u16(d_depth_raw, H * W, depth_scale, invalid_raw, &d_depth))) return rc;
+    return hash_run(h, d_rgb, d_depth, H, W, f, c, Tinv);
+}
+
+extern "C" int vh_frame_source(tsdf_hash *h, void *producer_stream)
+{
+    BAD_ARG(!h, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return h->io.adopt(static_cast<cudaStream_t>(producer_stream));
 }
 
 static int hash_fill_stats(tsdf_hash *h, const StatsBlock *st, int64_t frames, int64_t stats[12])

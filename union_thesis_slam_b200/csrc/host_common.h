@@ -50,8 +50,15 @@ struct VolumeGeom {
 
 int tsdf_select_device(int device, int *sm_count);
 
+// frame fan-out (capi_fanout.cu): ranks of one box and ring slots per rank
+#define FANOUT_MAX_WORLD 16
+#define FANOUT_MAX_SLOTS 8
+
 // Per-warp update counters owned by a handle (see UpdateCounters).
-#define FRAME_SLOTS 3 // frames in flight per handle: preparation of frame n+2 may start while frame n integrates
+#ifndef FRAME_SLOTS
+#define FRAME_SLOTS 3
+#endif
+// FRAME_SLOTS: frames in flight per handle: preparation of frame n+2 may start while frame n integrates
 struct CounterStore {
     unsigned long long *frame[FRAME_SLOTS] = {}; // one per frame slot
     unsigned long long *total = nullptr;
@@ -154,6 +161,15 @@ struct FrameIO {
     int upload_u16(const uint8_t *rgb, const uint16_t *depth_raw, int npix, double depth_scale, int invalid_raw,
                    const uint8_t **d_rgb_out, const double **d_depth_out);
     int finish_upload(); // waits until the copy engine has left the caller's buffers (end of an integrate call)
+    // A frame produced on the device by a stream of the caller (a collective's stream, a decoder): adopt()
+    // orders the next frame's preparation kernel after the work enqueued on `producer` so far; once that
+    // kernel has consumed the frame (release_upload_after_prep) `producer` is made to wait for it, so
+    // whatever the caller enqueues there next may overwrite the same buffers.
+    cudaStream_t ext = nullptr;
+    cudaEvent_t ext_ready = nullptr, ext_consumed = nullptr;
+    int adopt(cudaStream_t producer);
+    // raw uint16 depth already on the device: converted into the next upload slot's float64 image (stream `pre`)
+    int convert_u16(const uint16_t *d_raw, int npix, double depth_scale, int invalid_raw, const double **d_depth_out);
     int ensure_px(int npix);
     int set_subs(int n);              // prepared frames per slot (drains the streams when it grows)
     static int prep_index(int slot, int sub) { return sub * FRAME_SLOTS + slot; }

@@ -98,14 +98,29 @@ class TSDFVolume:
             float(obs_weight), float(depth_scale), int(invalid_raw)))
         self._host_cache = None
 
-    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
+    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1., producer_stream=None):
         """Frame already resident in HBM (torch uint8 [H,W,3] / float64 [H,W] tensors or raw
-        device pointers); ``tinv`` is the host-computed inverse pose."""
+        device pointers); ``tinv`` is the host-computed inverse pose.  ``producer_stream`` (a raw
+        cudaStream_t) names the stream that is still writing the buffers (see dist.FrameFanout)."""
         self._k_buf[...] = cam_intr
         self._tinv_buf[...] = tinv
+        if producer_stream is not None:
+            _capi.check(self._lib.tsdf_grid_frame_source(self._handle, producer_stream))
         _capi.check(self._lib.tsdf_grid_integrate_device(
             self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
+        self._host_cache = None
+
+    def integrate_device_raw(self, d_rgb, d_depth_raw, im_h, im_w, cam_intr, tinv, obs_weight=1., depth_scale=1000.,
+                             invalid_raw=65535, producer_stream=None):
+        """integrate_raw for a frame resident in HBM (uint8 colour, uint16 sensor depth)."""
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = tinv
+        if producer_stream is not None:
+            _capi.check(self._lib.tsdf_grid_frame_source(self._handle, producer_stream))
+        _capi.check(self._lib.tsdf_grid_integrate_device_u16(
+            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth_raw), im_h, im_w, self._k_ptr, self._tinv_ptr,
+            float(obs_weight), float(depth_scale), int(invalid_raw)))
         self._host_cache = None
 
     # -- read-out ------------------------------------------------------------------------------

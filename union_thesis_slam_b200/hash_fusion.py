@@ -113,12 +113,25 @@ class HashTable:
             self._handle, _capi.ptr(rgb), _capi.ptr(raw), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight), float(depth_scale), int(invalid_raw)))
 
-    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1.):
+    def integrate_device(self, d_rgb, d_depth, im_h, im_w, cam_intr, tinv, obs_weight=1., producer_stream=None):
+        """Frame resident in HBM; ``producer_stream``: see grid_fusion.TSDFVolume.integrate_device."""
         self._k_buf[...] = cam_intr
         self._tinv_buf[...] = tinv
+        if producer_stream is not None:
+            _capi.check(self._lib.vh_frame_source(self._handle, producer_stream))
         _capi.check(self._lib.vh_integrate_device(
             self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth), im_h, im_w, self._k_ptr, self._tinv_ptr,
             float(obs_weight)))
+
+    def integrate_device_raw(self, d_rgb, d_depth_raw, im_h, im_w, cam_intr, tinv, obs_weight=1., depth_scale=1000.,
+                             invalid_raw=65535, producer_stream=None):
+        self._k_buf[...] = cam_intr
+        self._tinv_buf[...] = tinv
+        if producer_stream is not None:
+            _capi.check(self._lib.vh_frame_source(self._handle, producer_stream))
+        _capi.check(self._lib.vh_integrate_device_u16(
+            self._handle, _capi.ptr(d_rgb), _capi.ptr(d_depth_raw), im_h, im_w, self._k_ptr, self._tinv_ptr,
+            float(obs_weight), float(depth_scale), int(invalid_raw)))
 
     # -- read-out ------------------------------------------------------------------------------
     def get_volume_with_weight(self):
