@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2 GPUs: new fan-out tests, the torchrun parity check, and a short N=2 bench (no configs / cpu).
 set -u
-timeout 900 python -m pytest tests/test_ingest_gpu.py tests/test_multi_gpu_spawn.py tests/test_dense_gpu.py tests/test_hash_gpu.py -x -q -m gpu > gpurun_out/r2t_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_multi_gpu_spawn.py -x -q -m gpu > gpurun_out/r2t_pytest.log 2>&1
 tail -5 gpurun_out/r2t_pytest.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
   bench.py --gpus 2 --steps 20 --warmup 5 --no-configs > gpurun_out/r2t_bench_n2.json 2> gpurun_out/r2t_bench_n2.err
