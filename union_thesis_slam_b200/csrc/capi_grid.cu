@@ -661,6 +661,8 @@ struct tsdf_grid {
 };
 
 static int grid_flush_batch(tsdf_grid *g);
+// entries behind a brick list that a persistent CTA may read before it knows the list's length (at most one per CTA)
+static const size_t LIST_PAD = 32 * 256;
 
 static int grid_free(tsdf_grid *g)
 {
@@ -719,7 +721,7 @@ extern "C" int tsdf_grid_create(const int64_t dim[3], const float origin[3], dou
     const size_t nb_alloc = std::max<size_t>(g->nbricks, 1);
     e = cudaMalloc(&g->bricks, nb_alloc * BRICK_FLOATS * sizeof(float));
     for (int i = 0; i < FRAME_SLOTS && e == cudaSuccess; ++i)
-        e = cudaMalloc(&g->vis_list[i], std::max<size_t>(g->classes * g->class_cap, 1) * sizeof(BrickRef));
+        e = cudaMalloc(&g->vis_list[i], (g->classes * g->class_cap + LIST_PAD) * sizeof(BrickRef));
     if (e == cudaSuccess) e = cudaMalloc(&g->tot, sizeof(Totals));
     if (e != cudaSuccess) {
         tsdf_set_error("device allocation of %.2f GB failed: %s", nb_alloc * 6144.0 / 1e9, cudaGetErrorString(e));

@@ -195,6 +195,9 @@ struct FrameBatch {
 #ifndef DENSE_BATCH_MIN_CTAS
 #define DENSE_BATCH_MIN_CTAS 12 // K > 1: 80 registers (the frame loop carries more state; 64 spills ~200 B)
 #endif
+#ifndef DENSE_FAST_START
+#define DENSE_FAST_START 1
+#endif
 #ifndef DENSE_SM_CONTIGUOUS
 #define DENSE_SM_CONTIGUOUS 1
 #endif
@@ -328,8 +331,22 @@ k_integrate_dense_v1(FrameParams f, VolumeParams v, const BrickRef *__restrict__
     s_updates[t] = 0; // only this thread touches its counter: no barrier needed
     int round = 0;
     int b = entry_of(0, n_sm);
+#if DENSE_FAST_START
+    // The first entry is requested together with the count (the list is padded by a grid's worth of entries, so
+    // the read is in bounds whatever the count turns out to be), and the first brick's record is on its way to
+    // L2 while the lattice -> pixel chain of its first quad runs: a persistent CTA of a small shard lives for
+    // only ~6 bricks, so its start-up chain of dependent loads is a visible part of the launch.
+    int4 br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
+    if (b < n) {
+        const float *r0 = bricks + (size_t)(uint32_t)br_next.w * BRICK_FLOATS + 8 * t;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + BRICK_VOX));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + 2 * BRICK_VOX));
+    }
+#else
     int4 br_next = make_int4(0, 0, 0, 0);
     if (b < n) br_next = __ldg(reinterpret_cast<const int4 *>(list) + b);
+#endif
     while (b < n) {
         const int4 br = br_next;
         b = entry_of(++round, n_sm);
