@@ -59,6 +59,21 @@ def test_no_device_fails_loudly(built):
         hash_fusion.HashTable(np.array([[0., 1.], [0., 1.], [0., 1.]]), 0.1)
     with pytest.raises(built.TSDFError):
         built.device_info(0)
+    h = C.c_void_p()
+    assert built.lib().tsdf_fanout_create(0, 0, 1, 1 << 20, 3, C.byref(h)) == -2 and not h.value
+
+
+def test_fanout_arguments_are_checked_before_any_device_work(built):
+    """Argument errors of the frame fan-out do not need a GPU to be reported."""
+    lib, h = built.lib(), C.c_void_p()
+    for device, rank, world, nbytes, slots in ((0, 0, 17, 1 << 20, 3), (0, 2, 2, 1 << 20, 3), (0, 0, 1, 1 << 20, 0),
+                                               (0, 0, 1, 1 << 20, 9), (0, 0, 1, 0, 3)):
+        assert lib.tsdf_fanout_create(device, rank, world, nbytes, slots, C.byref(h)) == -1
+        assert not h.value and lib.tsdf_last_error()
+    assert lib.tsdf_fanout_create(0, 0, 1, 1 << 20, 3, None) == -1
+    assert lib.tsdf_fanout_push(None, 0, None, 0, None, 0, 0) == -1
+    assert lib.tsdf_fanout_integrate(None, None, None, 0, 0, None, None, 4, 4, 0, None, None, 1.0, 1000.0, -1) == -1
+    assert lib.tsdf_fanout_destroy(None) == 0
 
 
 def test_product_never_imports_the_oracle():
