@@ -56,6 +56,14 @@ def main():
             mine = fan_c.source_of(fan_c.frames) == rank
             fan_c.integrate(c if mine else None, d if mine else None, case["K"], p, obs_weight=obs)
     fan_c.drain()
+    # one rank owns the camera (every frame from rank 0) and the ring has a single slot: the source may not
+    # overwrite it before every peer has pulled, and no peer may pull before the upload is through
+    vol_s = grid_fusion.TSDFVolume(case["vol_bnds"].copy(), 0.02)
+    fan_s = tdist.FrameFanout(vol_s, im_h, im_w, slots=1)
+    for rep in range(3):
+        for c, d, p, obs in case["frames"]:
+            fan_s.integrate(c if rank == 0 else None, d if rank == 0 else None, case["K"], p, obs_weight=obs, src=0)
+    fan_s.drain()
     t, c_ = vol.get_volume()
     w = vol._weight_vol_cpu
     ok = (np.array_equal(t, orc._tsdf_vol_cpu) and np.array_equal(w, orc._weight_vol_cpu)
@@ -68,7 +76,9 @@ def main():
     ok_f = ok_f and np.array_equal(hf_t, t) and np.array_equal(hf_w, w) and np.array_equal(hf_c, c_)
     tc, cc = vol_c.get_volume()
     ok_f = ok_f and np.array_equal(tc, t) and np.array_equal(cc, c_) and np.array_equal(vol_c._weight_vol_cpu, w)
-    fan_v.close(); fan_h.close()
+    ts, cs = vol_s.get_volume()
+    ok_f = ok_f and np.array_equal(ts, t) and np.array_equal(cs, c_) and np.array_equal(vol_s._weight_vol_cpu, w)
+    fan_v.close(); fan_h.close(); fan_s.close()
     nblk = torch.tensor([ht.stats()["blocks"]], device="cuda")
     dist.all_reduce(nblk)
     want = len(oracle.block_set_from_weight(orc._weight_vol_cpu))
