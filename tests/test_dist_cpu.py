@@ -227,3 +227,19 @@ def test_frame_fanout_rotates_the_upload_rank():
     assert [fan.source_of(i) for i in range(9)] == [0, 1, 2, 3, 0, 1, 2, 3, 0]
     with pytest.raises(ValueError):
         fan.integrate(None, None, np.eye(3), np.eye(4), src=4)
+
+
+def test_frame_fanout_rejects_what_it_cannot_do():
+    with pytest.raises(ValueError):   # frames move between GPUs on the peer transport
+        tdist.FrameFanout(_RecordingMap(0, 1), 4, 4, device="cpu", transport="peer")
+    with pytest.raises(ValueError):
+        tdist.FrameFanout(_RecordingMap(0, 1), 4, 4, device="cpu", transport="carrier-pigeon")
+    fan = tdist.FrameFanout(_RecordingMap(0, 1), 4, 6, device="cpu")
+    assert fan.transport == "collective" and fan.slots == 3 and fan.payload_bytes() == 4 * 6 * 11
+    with pytest.raises(ValueError):   # wrong image size
+        fan.integrate(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4)), np.eye(3), np.eye(4))
+    # a one-rank fan-out is the plain hand-over of a staged frame
+    fan.integrate(np.full((4, 6, 3), 7, np.uint8), np.full((4, 6), 1.5), np.eye(3), np.eye(4), obs_weight=2.0)
+    rgb, depth, tinv, w = fan.target.got[0]
+    assert (rgb == 7).all() and (depth == 1.5).all() and np.array_equal(tinv, np.eye(4)) and w == 2.0
+    fan.close()
