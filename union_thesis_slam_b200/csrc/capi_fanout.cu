@@ -26,10 +26,12 @@
 
 struct FanFlags {
     uint32_t error;                     // set by a wait kernel that timed out
-    uint32_t pad[63];
+    uint32_t pad[119];                  // the ring slots behind the flags start on a 1 KiB boundary
     uint32_t ready[FANOUT_MAX_SLOTS]; // sequence number + 1 of the frame its source has staged in ITS copy of the slot
     uint32_t pulled[FANOUT_MAX_SLOTS][FANOUT_MAX_WORLD]; // [slot][rank]: last frame rank has pulled from THIS arena's slot, + 1
 };
+
+static_assert(sizeof(FanFlags) == 1024, "ring slots must stay 256-byte aligned");
 
 struct PeerFlagPtrs {
     uint32_t *p[FANOUT_MAX_WORLD];
